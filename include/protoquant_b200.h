@@ -1,0 +1,129 @@
+/*
+ * protoquant_b200 — C ABI of the B200 (sm_100a) dynamic-quantized linear path.
+ *
+ * This is the drop-in boundary for protoquant's dynamic int8 linear path
+ * (BASELINE.json north_star).  The reference checkout is ABSENT in this
+ * environment (/root/reference holds only CODE_OF_CONDUCT.md),
+ * so no reference file:line can be cited; each entry point instead cites the
+ * SURVEY.md §8 row it implements.  The Python side (protoquant_b200/*.py) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all buffers; nothing is allocated or freed here, except
+ *     the opaque pq_linear handle of the host-buffer convenience API;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     function synchronises unless it says so;
+ *   - return value 0 = ok, non-zero = PQ_ERR_*; pq_last_error() returns a
+ *     thread-local message for the last non-zero return;
+ *   - dtype codes: PQ_F32 / PQ_F16 / PQ_BF16 (/ PQ_I32 for raw accumulators).
+ *   - no CPU fallback exists: on a machine without an sm_100 device the
+ *     compute entry points return PQ_ERR_DEVICE.
+ */
+#ifndef PROTOQUANT_B200_H
+#define PROTOQUANT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQ_VERSION 100 /* 0.1.0 */
+
+enum pq_dtype { PQ_F32 = 0, PQ_F16 = 1, PQ_BF16 = 2, PQ_I32 = 3 };
+
+enum pq_status {
+  PQ_OK = 0,
+  PQ_ERR_ARG = 1,      /* bad shape / stride / dtype / null pointer            */
+  PQ_ERR_ALIGN = 2,    /* pointer or leading dimension not aligned as required */
+  PQ_ERR_DEVICE = 3,   /* no CUDA device, or device is not sm_100              */
+  PQ_ERR_CUDA = 4,     /* a CUDA runtime/driver call failed                    */
+  PQ_ERR_UNSUPPORTED = 5
+};
+
+/* Scale-computation variants (SURVEY.md §8c "knobs").  Default = PQ_DIV. */
+enum pq_scale_mode {
+  PQ_DIV = 0,      /* s = amax/127 ; q = rne(x / s)          (true IEEE division)  */
+  PQ_RCP_MUL = 1,  /* s = amax/127 ; q = rne(x * (1/s))      (torch.ao per-token)  */
+  PQ_INV_SCALE = 2 /* s = amax/127 ; q = rne(x * (127/amax))                       */
+};
+
+typedef struct pq_quant_spec {
+  int32_t scale_mode; /* enum pq_scale_mode                                        */
+  float eps;          /* 0 = none; else s = max(amax, eps)/127 (torch.ao: 1e-5)    */
+  int32_t qmin;       /* -128 (default) or -127                                    */
+} pq_quant_spec;
+
+int pq_version(void);
+const char* pq_last_error(void);
+
+/* Number of CUDA kernels this library has launched in the calling process
+ * (all threads).  bench.py reports it as "gpu_launches". */
+uint64_t pq_launch_count(void);
+
+/* SURVEY §8 row a1 — per-token (row-wise) symmetric int8 quantizer.
+ *   x   [M,K]  x_dtype, row stride ldx (elements)
+ *   xq  [M,K]  int8,    row stride ldq (bytes)      (transpose == 0)
+ *       [K,M]  int8,    row stride ldq (bytes)      (transpose != 0)
+ *   s_x [M]    fp32
+ * spec may be NULL (= {PQ_DIV, 0, -128}).  Requires K >= 1, M >= 0. */
+int pq_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
+                 int8_t* xq, int64_t ldq, float* s_x, int transpose,
+                 const pq_quant_spec* spec, void* stream);
+
+/* SURVEY §8 row a2 — per-output-channel int8 weight quantizer (run once at load).
+ *   W [N,K] w_dtype row stride ldw;  Wq [N,K] int8 row stride ldwq;  s_w [N] fp32. */
+int pq_weight_quant(const void* W, int w_dtype, int64_t N, int64_t K, int64_t ldw,
+                    int8_t* Wq, int64_t ldwq, float* s_w,
+                    const pq_quant_spec* spec, void* stream);
+
+/* SURVEY §8 rows a3+a4 — int8 x int8 -> int32 GEMM on tcgen05 with the fused
+ * dequant epilogue  y[m,n] = cast( (float(acc[m,n]) * s_x[m]) * s_w[n] + bias[n] ).
+ *   xq [M,K] int8 row stride lda (bytes, multiple of 16, base 16-B aligned)
+ *   Wq [N,K] int8 row stride ldb (bytes, multiple of 16, base 16-B aligned)
+ *   bias [N] fp32 or NULL;  y [M,N] y_dtype (PQ_BF16/PQ_F16/PQ_F32) row stride ldy (elements). */
+int pq_qgemm(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
+             const float* s_x, const float* s_w, const float* bias,
+             void* y, int y_dtype, int64_t ldy,
+             int64_t M, int64_t N, int64_t K, void* stream);
+
+/* Parity hook for row a3: raw int32 accumulators acc[M,N], row stride ldc (elements). */
+int pq_qgemm_i32(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
+                 int32_t* acc, int64_t ldc,
+                 int64_t M, int64_t N, int64_t K, void* stream);
+
+/* SURVEY §8 row a5 — QTensor.dequantize():  out[r,c] = q[r,c] * s[axis==0 ? r : c]. */
+int pq_dequant(const int8_t* q, int64_t ldq, const float* s, int axis,
+               void* out, int out_dtype, int64_t ldo,
+               int64_t rows, int64_t cols, void* stream);
+
+/* SURVEY §8 row a6 — one dynamic-quant linear forward on device buffers:
+ * act-quant into caller workspace (xq_ws [M, round_up(K,16)] int8, sx_ws [M] fp32)
+ * followed by pq_qgemm.  Two kernel launches, no sync. */
+int pq_qlinear(const void* x, int x_dtype, int64_t ldx,
+               const int8_t* Wq, int64_t ldb, const float* s_w, const float* bias,
+               void* y, int y_dtype, int64_t ldy,
+               int8_t* xq_ws, float* sx_ws,
+               int64_t M, int64_t N, int64_t K,
+               const pq_quant_spec* spec, void* stream);
+
+/* Host-buffer convenience API (what bench.py's "e2e" number goes through).
+ * A pq_linear owns device copies of (Wq, s_w, bias), a device activation/output
+ * workspace for up to max_tokens rows, and a private stream. */
+typedef struct pq_linear pq_linear;
+
+/* W_host [N,K] row-major w_dtype, bias_host [N] fp32 or NULL.  Quantizes on the GPU. */
+int pq_linear_create(pq_linear** out, const void* W_host, int w_dtype,
+                     int64_t N, int64_t K, const float* bias_host,
+                     int64_t max_tokens, int act_dtype, int out_dtype,
+                     const pq_quant_spec* spec);
+/* x_host [M,K] act_dtype (pinned or pageable), y_host [M,N] out_dtype.
+ * H2D copy + act-quant + qgemm + D2H copy on the handle's stream, then waits for it. */
+int pq_linear_forward_host(pq_linear* h, const void* x_host, void* y_host, int64_t M);
+void pq_linear_destroy(pq_linear* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTOQUANT_B200_H */

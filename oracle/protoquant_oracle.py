@@ -1,0 +1,186 @@
+"""CPU oracle for protoquant's dynamic-quantized linear path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product
+(``protoquant_b200``) never does: it has no CPU path at all.
+
+PARITY UNPINNED.  The reference checkout is absent in this environment
+(``/root/reference`` holds only CODE_OF_CONDUCT.md — SURVEY.md §0), so no
+reference file:line, test or golden vector exists to pin this restatement
+against protoquant itself.  What it follows instead:
+
+* BASELINE.json ``north_star``: per-token absmax -> scale -> round-to-nearest-even
+  int8 for activations; per-output-channel int8 + scale for weights; exact
+  int8 x int8 -> int32; epilogue ``row scale x column scale, bias, cast``.
+* SURVEY.md §8c "SPEC v0" (frozen default, every item a knob):
+  upcast to fp32 · amax = max|x| over the last dim · s = amax/127 (fp32 true
+  division) · amax == 0 -> s = 1 · q = rne(x / s) · clamp [-128,127] · scales
+  stored fp32 · epilogue ((float(acc)*s_x)*s_w)+bias in fp32, one RNE cast.
+* The nearest *verifiable* definition in this container, a different project:
+  ``torch.ao.quantization.fx._decomposed`` ``choose_qparams_per_token`` (:778-810)
+  and ``quantize_per_token`` (:930-965).  ``QuantSpec.torch_ao()`` selects the knob
+  values that reproduce it bit-exactly; ``tests/golden/make_golden.py`` generated the
+  committed golden vectors from those torch ops, and ``tests/test_oracle.py`` pins
+  this oracle against them.
+
+All arithmetic is explicit numpy float32 (no fused multiply-add, no fast-math).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional, Tuple
+
+import numpy as np
+
+try:  # torch is used only for bf16 <-> fp32 conversion and a fast exact int32 matmul
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+DIV, RCP_MUL, INV_SCALE = 0, 1, 2
+
+
+@dataclasses.dataclass(frozen=True)
+class QuantSpec:
+    """Knobs of SURVEY.md §8c.  Default == SPEC v0."""
+
+    scale_mode: int = DIV   # DIV: x / s ; RCP_MUL: x * (1/s) ; INV_SCALE: x * (127/amax)
+    eps: float = 0.0        # 0 = none; else amax is clamped to >= eps before /127
+    qmin: int = -128        # -128 or -127
+    qmax: int = 127
+
+    @staticmethod
+    def torch_ao() -> "QuantSpec":
+        # torch/ao/quantization/fx/_decomposed.py:808 clamp(min=1e-5)/127, :959 x*(1/scale)
+        return QuantSpec(scale_mode=RCP_MUL, eps=1e-5, qmin=-128)
+
+
+SPEC_V0 = QuantSpec()
+
+
+def to_f32(x) -> np.ndarray:
+    """Exact upcast of fp32 / fp16 / bf16 input (numpy array or torch tensor) to float32."""
+    if torch is not None and isinstance(x, torch.Tensor):
+        return x.detach().to("cpu").to(torch.float32).numpy()
+    x = np.asarray(x)
+    if x.dtype == np.float32:
+        return x
+    if x.dtype == np.float16:
+        return x.astype(np.float32)
+    raise TypeError(f"unsupported input dtype {x.dtype}")
+
+
+def rowwise_scale(x32: np.ndarray, spec: QuantSpec = SPEC_V0) -> Tuple[np.ndarray, np.ndarray]:
+    """(amax_eff, scale) per row of a [R, C] float32 matrix."""
+    amax = np.max(np.abs(x32), axis=-1).astype(np.float32) if x32.shape[-1] else np.zeros(x32.shape[:-1], np.float32)
+    if spec.eps > 0:
+        amax = np.maximum(amax, np.float32(spec.eps))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = (amax / np.float32(127.0)).astype(np.float32)
+    s = np.where(amax == 0, np.float32(1.0), s).astype(np.float32)
+    return amax, s
+
+
+def quantize_rowwise(x, spec: QuantSpec = SPEC_V0) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-row symmetric int8 quantisation of a 2-D matrix.  Returns (q int8 [R,C], s fp32 [R]).
+
+    Used both for activations (rows = tokens) and for weights
+    W[N,K] (rows = output channels, row a2)."""
+    x32 = to_f32(x)
+    assert x32.ndim == 2
+    amax, s = rowwise_scale(x32, spec)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if spec.scale_mode == DIV:
+            r = (x32 / s[:, None]).astype(np.float32)
+        elif spec.scale_mode == RCP_MUL:
+            inv = (np.float32(1.0) / s).astype(np.float32)
+            r = (x32 * inv[:, None]).astype(np.float32)
+        elif spec.scale_mode == INV_SCALE:
+            inv = np.where(amax == 0, np.float32(1.0), np.float32(127.0) / np.where(amax == 0, np.float32(1), amax)).astype(np.float32)
+            r = (x32 * inv[:, None]).astype(np.float32)
+        else:
+            raise ValueError(spec.scale_mode)
+    q = np.rint(r)  # round half to even
+    q = np.clip(q, spec.qmin, spec.qmax)
+    return q.astype(np.int8), s
+
+
+def quantize_act(x, spec: QuantSpec = SPEC_V0, transpose: bool = False):
+    q, s = quantize_rowwise(x, spec)
+    return (np.ascontiguousarray(q.T) if transpose else q), s
+
+
+def quantize_weight(w, spec: QuantSpec = SPEC_V0):
+    return quantize_rowwise(w, spec)
+
+
+def int_mm(xq: np.ndarray, wq: np.ndarray) -> np.ndarray:
+    """Exact acc[m,n] = sum_k xq[m,k] * wq[n,k] in int32 (row a3)."""
+    xq = np.ascontiguousarray(xq, dtype=np.int8)
+    wq = np.ascontiguousarray(wq, dtype=np.int8)
+    M, K = xq.shape
+    N, K2 = wq.shape
+    assert K == K2
+    if torch is not None and M > 16 and K % 8 == 0 and N % 8 == 0:
+        # torch._int_mm on CPU is exact int32 accumulation (torch/_meta_registrations.py:3762)
+        return torch._int_mm(torch.from_numpy(xq), torch.from_numpy(wq).t()).numpy()
+    return xq.astype(np.int32) @ wq.astype(np.int32).T
+
+
+def dequant_epilogue(acc: np.ndarray, s_x: np.ndarray, s_w: np.ndarray,
+                     bias: Optional[np.ndarray] = None) -> np.ndarray:
+    """fp32 result of ((float(acc) * s_x[m]) * s_w[n]) + bias[n]  (row a4, before the cast)."""
+    y = acc.astype(np.float32)
+    y = (y * s_x.astype(np.float32)[:, None]).astype(np.float32)
+    y = (y * s_w.astype(np.float32)[None, :]).astype(np.float32)
+    if bias is not None:
+        y = (y + bias.astype(np.float32)[None, :]).astype(np.float32)
+    return y
+
+
+def cast_out(y32: np.ndarray, dtype: str):
+    """Single RNE cast of the fp32 epilogue result.  Returns a torch tensor for bf16/fp16."""
+    if dtype in ("f32", "float32"):
+        return torch.from_numpy(y32) if torch is not None else y32
+    t = torch.from_numpy(np.ascontiguousarray(y32))
+    if dtype in ("bf16", "bfloat16"):
+        return t.to(torch.bfloat16)
+    if dtype in ("f16", "float16"):
+        return t.to(torch.float16)
+    raise ValueError(dtype)
+
+
+def dequantize(q: np.ndarray, s: np.ndarray, axis: int = 0) -> np.ndarray:
+    """QTensor.dequantize(): q * s broadcast along `axis` (0: per-row, 1: per-column), fp32 (row a5)."""
+    q32 = q.astype(np.float32)
+    s = s.astype(np.float32)
+    return (q32 * (s[:, None] if axis == 0 else s[None, :])).astype(np.float32)
+
+
+def qlinear(x, wq: np.ndarray, s_w: np.ndarray, bias: Optional[np.ndarray] = None,
+            spec: QuantSpec = SPEC_V0, out_dtype: str = "bf16"):
+    """The whole forward of row a6: act-quant -> int32 GEMM -> dequant epilogue -> cast."""
+    x32 = to_f32(x)
+    lead = x32.shape[:-1]
+    x2 = x32.reshape(-1, x32.shape[-1])
+    xq, s_x = quantize_rowwise(x2, spec)
+    acc = int_mm(xq, wq)
+    y = cast_out(dequant_epilogue(acc, s_x, s_w, bias), out_dtype)
+    return y.reshape(*lead, wq.shape[0])
+
+
+# ---- torch-threaded variant used only as the timed CPU baseline (bench.py) ----------
+def qlinear_torch_cpu(x_t, wq_t_kn, s_w_t, bias_t, out_dtype):
+    """Same math as `qlinear` written with torch CPU ops so it uses every host thread.
+    x_t [M,K] float tensor; wq_t_kn = Wq.t() ([K,N] int8 view); returns [M,N] out_dtype."""
+    xf = x_t.to(torch.float32)
+    amax = xf.abs().amax(dim=-1, keepdim=True)
+    s = amax / 127.0
+    s = torch.where(amax == 0, torch.ones_like(s), s)
+    xq = torch.round(xf / s).clamp_(-128, 127).to(torch.int8)
+    acc = torch._int_mm(xq, wq_t_kn)
+    y = acc.to(torch.float32) * s
+    y = y * s_w_t[None, :]
+    if bias_t is not None:
+        y = y + bias_t[None, :]
+    return y.to(out_dtype)

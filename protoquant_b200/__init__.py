@@ -1,0 +1,19 @@
+"""protoquant_b200 — B200-native (sm_100a) dynamic-quantized int8 linear path.
+
+Python surface over the C ABI in include/protoquant_b200.h.
+No Triton, no backend dispatch, no CPU fallback.
+"""
+from ._lib import ProtoquantError, launch_count, lib
+from .functional import (DEFAULT_SPEC, QuantSpec, dequantize as dequantize_tensor, qgemm, qgemm_i32, qlinear,
+                         quantize_act, quantize_weight)
+from .qlinear import DynamicQuantLinear, swap_linear
+from .qtensor import QTensor, dequantize, quantize
+from .sharded import ShardedDynamicQuantLinear, maybe_shard, shard_bounds
+
+__version__ = "0.1.0"
+__all__ = [
+    "ProtoquantError", "launch_count", "lib", "QuantSpec", "DEFAULT_SPEC",
+    "quantize_act", "quantize_weight", "qgemm", "qgemm_i32", "qlinear", "dequantize_tensor",
+    "QTensor", "quantize", "dequantize", "DynamicQuantLinear", "swap_linear",
+    "ShardedDynamicQuantLinear", "maybe_shard", "shard_bounds",
+]

@@ -1,0 +1,95 @@
+"""ctypes binding of libprotoquant_b200.so (the C ABI in include/protoquant_b200.h).
+
+There is no fallback: if the shared library has not been built, or the process has no
+sm_100 GPU, every entry point raises.  Build with ``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C protoquant_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprotoquant_b200.so")
+
+PQ_F32, PQ_F16, PQ_BF16, PQ_I32 = 0, 1, 2, 3
+PQ_DIV, PQ_RCP_MUL, PQ_INV_SCALE = 0, 1, 2
+
+# every symbol include/protoquant_b200.h declares (tests/test_abi.py checks the .so exports them)
+EXPORTS = (
+    "pq_version", "pq_last_error", "pq_launch_count", "pq_act_quant", "pq_weight_quant",
+    "pq_qgemm", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
+    "pq_linear_create", "pq_linear_forward_host", "pq_linear_destroy",
+)
+
+
+class PQQuantSpec(ctypes.Structure):
+    _fields_ = [("scale_mode", ctypes.c_int32), ("eps", ctypes.c_float), ("qmin", ctypes.c_int32)]
+
+
+class ProtoquantError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i64, i32 = c.c_void_p, c.c_int64, c.c_int
+    specp = c.POINTER(PQQuantSpec)
+    lib.pq_version.restype = i32
+    lib.pq_version.argtypes = []
+    lib.pq_last_error.restype = c.c_char_p
+    lib.pq_last_error.argtypes = []
+    lib.pq_launch_count.restype = c.c_uint64
+    lib.pq_launch_count.argtypes = []
+    lib.pq_act_quant.restype = i32
+    lib.pq_act_quant.argtypes = [vp, i32, i64, i64, i64, vp, i64, vp, i32, specp, vp]
+    lib.pq_weight_quant.restype = i32
+    lib.pq_weight_quant.argtypes = [vp, i32, i64, i64, i64, vp, i64, vp, specp, vp]
+    lib.pq_qgemm.restype = i32
+    lib.pq_qgemm.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp]
+    lib.pq_qgemm_i32.restype = i32
+    lib.pq_qgemm_i32.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
+    lib.pq_dequant.restype = i32
+    lib.pq_dequant.argtypes = [vp, i64, vp, i32, vp, i32, i64, i64, i64, vp]
+    lib.pq_qlinear.restype = i32
+    lib.pq_qlinear.argtypes = [vp, i32, i64, vp, i64, vp, vp, vp, i32, i64, vp, vp, i64, i64, i64, specp, vp]
+    lib.pq_linear_create.restype = i32
+    lib.pq_linear_create.argtypes = [c.POINTER(vp), vp, i32, i64, i64, vp, i64, i32, i32, specp]
+    lib.pq_linear_forward_host.restype = i32
+    lib.pq_linear_forward_host.argtypes = [vp, vp, vp, i64]
+    lib.pq_linear_destroy.restype = None
+    lib.pq_linear_destroy.argtypes = [vp]
+    if hasattr(lib, "pq_debug_set_gemm_config"):
+        lib.pq_debug_set_gemm_config.restype = None
+        lib.pq_debug_set_gemm_config.argtypes = [i32]
+
+
+def lib():
+    """The loaded shared library; raises ProtoquantError if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ProtoquantError(
+                        f"{LIB_PATH} not found: the CUDA extension is not built and protoquant_b200 "
+                        "has no CPU fallback. Run __graft_entry__.build() (or make -C protoquant_b200/csrc).")
+                handle = ctypes.CDLL(LIB_PATH)
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().pq_last_error()
+        raise ProtoquantError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(lib().pq_launch_count())

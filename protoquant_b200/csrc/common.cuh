@@ -1,0 +1,64 @@
+// Shared host/device helpers for the protoquant_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/protoquant_b200.h"
+
+namespace pq {
+
+// ---- error plumbing (thread-local message, see pq_last_error) -------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define PQ_FAIL(code, ...)        \
+  do {                            \
+    ::pq::set_error(__VA_ARGS__); \
+    return (code);                \
+  } while (0)
+
+#define PQ_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      PQ_FAIL(PQ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+              __FILE__, __LINE__);                                                     \
+  } while (0)
+
+// Checks that the current device is an sm_100 part; caches the answer per device.
+int check_device(int* num_sms);
+
+inline pq_quant_spec resolve_spec(const pq_quant_spec* s) {
+  pq_quant_spec d;
+  d.scale_mode = PQ_DIV;
+  d.eps = 0.f;
+  d.qmin = -128;
+  return s ? *s : d;
+}
+
+inline int dtype_size(int dt) {
+  switch (dt) {
+    case PQ_F32: return 4;
+    case PQ_F16: return 2;
+    case PQ_BF16: return 2;
+    case PQ_I32: return 4;
+    default: return 0;
+  }
+}
+
+// ---- internal launchers shared between translation units ------------------------
+int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
+                         int8_t* xq, int64_t ldq, float* s, int transpose,
+                         const pq_quant_spec& spec, cudaStream_t stream);
+
+int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
+                 const float* s_x, const float* s_w, const float* bias,
+                 void* out, int out_dtype, int64_t ldo,
+                 int64_t M, int64_t N, int64_t K, cudaStream_t stream);
+
+}  // namespace pq

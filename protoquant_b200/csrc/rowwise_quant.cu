@@ -1,0 +1,402 @@
+// Row-wise symmetric int8 quantizer.
+//
+//   amax[m] = max_k |x[m,k]|            (fp32, after an exact upcast of bf16/fp16)
+//   s[m]    = amax/127                  (fp32 IEEE division; amax == 0 -> s = 1)
+//   q[m,k]  = rne(x[m,k] / s[m])        (fp32 IEEE division, then round-half-even)
+//
+// The kernel is HBM-bound: 16-byte loads, the whole row kept in registers between
+// the absmax pass and the quantize pass (one global read, one global write), warp
+// shuffles + one smem hop for the row reduction.  Algorithmic bytes per row:
+// K*sizeof(in) + K + 4.
+//
+// Exactness.  A true `div.rn.f32` per element costs ~10 issue slots plus a branch,
+// which would make this kernel issue-bound at 6.5 TB/s.  Instead, per row we form
+// y = RN(1/s) once and per element
+//     q0 = RN(x*y);  r = fma(-q0, s, x);  q1 = fma(r, y, q0)
+// which is the classic FMA division step: q1 == RN(x/s) whenever no intermediate
+// underflows.  tools/check_fma_div.c proves rne(q1) == rne(x/s) exhaustively for
+// every (amax, x) pair of bf16 and of fp16 inputs with s in [2^-100, 2^100]; rows
+// whose scale falls outside [2^-60, 2^60] take the `div.rn.f32` path instead.
+// The final round-half-even to integer is done with the 1.5*2^23 magic add, whose
+// low mantissa byte is the two's complement int8 (|q1| <= 127.01 always, so the
+// [-128,127] clamp of the reference formula can never fire for finite input).
+#include "common.cuh"
+#include <type_traits>
+
+namespace pq {
+namespace {
+
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+
+template <typename T> struct VecTraits;
+template <> struct VecTraits<float> { static constexpr int EPV = 4; };
+template <> struct VecTraits<__half> { static constexpr int EPV = 8; };
+template <> struct VecTraits<__nv_bfloat16> { static constexpr int EPV = 8; };
+
+__device__ __forceinline__ uint4 ld_stream_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---- unpack a 16-byte vector to fp32 -------------------------------------------
+template <typename T> __device__ __forceinline__ void unpack(const uint4& v, float* f);
+template <> __device__ __forceinline__ void unpack<float>(const uint4& v, float* f) {
+  f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+  f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+}
+template <> __device__ __forceinline__ void unpack<__nv_bfloat16>(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <> __device__ __forceinline__ void unpack<__half>(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+    const float2 t = __half22float2(h);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+
+// ---- |.|-max of a 16-byte vector, returned as fp32 -----------------------------
+template <typename T> __device__ __forceinline__ float vec_absmax(const uint4& v, float m);
+template <> __device__ __forceinline__ float vec_absmax<float>(const uint4& v, float m) {
+  m = fmaxf(m, fabsf(__uint_as_float(v.x))); m = fmaxf(m, fabsf(__uint_as_float(v.y)));
+  m = fmaxf(m, fabsf(__uint_as_float(v.z))); m = fmaxf(m, fabsf(__uint_as_float(v.w)));
+  return m;
+}
+// For 16-bit floats |x| ordering == ordering of the 15 magnitude bits as integers, so
+// the max is taken on packed u16 lanes (exact) and converted once at the end.
+__device__ __forceinline__ uint32_t absmax_u16x2(const uint4& v, uint32_t m) {
+  m = __vmaxu2(m, v.x & 0x7fff7fffu); m = __vmaxu2(m, v.y & 0x7fff7fffu);
+  m = __vmaxu2(m, v.z & 0x7fff7fffu); m = __vmaxu2(m, v.w & 0x7fff7fffu);
+  return m;
+}
+template <typename T> __device__ __forceinline__ float u16_mag_to_float(uint32_t packed);
+template <> __device__ __forceinline__ float u16_mag_to_float<__nv_bfloat16>(uint32_t p) {
+  const uint32_t m = max(p & 0xffffu, p >> 16);
+  return __uint_as_float(m << 16);
+}
+template <> __device__ __forceinline__ float u16_mag_to_float<__half>(uint32_t p) {
+  const uint32_t m = max(p & 0xffffu, p >> 16);
+  return __half2float(__ushort_as_half((unsigned short)m));
+}
+template <> __device__ __forceinline__ float u16_mag_to_float<float>(uint32_t) { return 0.f; }
+
+// ---- per-row quantisation parameters --------------------------------------------
+struct RowQ {
+  float s;      // stored scale
+  float mul;    // RN(1/s) (DIV fast path, RCP_MUL) or RN(127/amax) (INV_SCALE)
+  int path;     // 0 = fma-division, 1 = div.rn, 2 = single multiply
+};
+
+__device__ __forceinline__ RowQ make_rowq(float amax, int scale_mode, float eps) {
+  RowQ r;
+  const float a = (eps > 0.f) ? fmaxf(amax, eps) : amax;
+  float s = __fdiv_rn(a, 127.0f);
+  if (a == 0.f) s = 1.0f;
+  r.s = s;
+  if (scale_mode == PQ_DIV) {
+    const bool safe = (s >= 0x1p-60f) && (s <= 0x1p60f);
+    r.path = safe ? 0 : 1;
+    r.mul = __frcp_rn(s);
+  } else if (scale_mode == PQ_RCP_MUL) {
+    r.path = 2;
+    r.mul = __frcp_rn(s);
+  } else {
+    r.path = 2;
+    r.mul = (a == 0.f) ? 1.0f : __fdiv_rn(127.0f, a);
+  }
+  return r;
+}
+
+// returns a float whose low mantissa byte is the int8 code
+__device__ __forceinline__ float quant_fast(float x, const RowQ& r) {
+  const float q0 = __fmul_rn(x, r.mul);
+  const float rem = __fmaf_rn(-q0, r.s, x);
+  const float q1 = __fmaf_rn(rem, r.mul, q0);
+  return __fadd_rn(q1, kMagic);
+}
+__device__ __forceinline__ float quant_div(float x, const RowQ& r) {
+  return __fadd_rn(__fdiv_rn(x, r.s), kMagic);
+}
+__device__ __forceinline__ float quant_mul(float x, const RowQ& r) {
+  return __fadd_rn(__fmul_rn(x, r.mul), kMagic);
+}
+__device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d) {
+  const uint32_t lo = __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x0040);
+  const uint32_t hi = __byte_perm(__float_as_uint(c), __float_as_uint(d), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ int8_t code_of(float magic_sum) {
+  return (int8_t)(__float_as_uint(magic_sum) & 0xffu);
+}
+
+template <int PATH>
+__device__ __forceinline__ float quant_one(float x, const RowQ& r) {
+  if (PATH == 0) return quant_fast(x, r);
+  if (PATH == 1) return quant_div(x, r);
+  return quant_mul(x, r);
+}
+
+// ---- vectorised, register-resident kernel ----------------------------------------
+// TPR threads cooperate on one row; each holds up to VPT 16-byte vectors of it.
+template <typename T, int TPR, int VPT>
+__global__ void __launch_bounds__((TPR > 256 ? TPR : 256))
+rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t ldx,
+                         int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
+                         int scale_mode, float eps) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr int THREADS = (TPR > 256 ? TPR : 256);
+  constexpr int ROWS = THREADS / TPR;
+  constexpr int WPR = (TPR + 31) / 32;  // warps per row
+  __shared__ float red[ROWS][WPR > 1 ? WPR : 1];
+
+  const int tid = threadIdx.x;
+  const int row_in_cta = tid / TPR;
+  const int t = tid % TPR;
+  const int64_t row = (int64_t)blockIdx.x * ROWS + row_in_cta;
+  const bool row_ok = row < M;
+
+  const T* xr = x + (row_ok ? row : 0) * ldx;
+  uint4 v[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = t + i * TPR;
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (row_ok && vi < nvec) v[i] = ld_stream_16(xr + (int64_t)vi * EPV);
+  }
+
+  float amax = 0.f;
+  if (sizeof(T) == 2) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) m = absmax_u16x2(v[i], m);
+    amax = u16_mag_to_float<T>(m);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) amax = vec_absmax<float>(v[i], amax);
+  }
+#pragma unroll
+  for (int o = (TPR < 32 ? TPR : 32) / 2; o > 0; o >>= 1)
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (WPR > 1) {
+    if ((t & 31) == 0) red[row_in_cta][t >> 5] = amax;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) amax = fmaxf(amax, red[row_in_cta][w]);
+  }
+
+  const RowQ rq = make_rowq(amax, scale_mode, eps);
+  if (row_ok && t == 0) s_out[row] = rq.s;
+  if (!row_ok) return;
+
+  int8_t* qr = xq + row * ldq;
+  auto emit = [&](auto path_tag) {
+    constexpr int PATH = decltype(path_tag)::value;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = t + i * TPR;
+      if (vi < nvec) {
+        float f[EPV];
+        unpack<T>(v[i], f);
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) f[j] = quant_one<PATH>(f[j], rq);
+        if (EPV == 8) {
+          uint2 o;
+          o.x = pack4(f[0], f[1], f[2], f[3]);
+          o.y = pack4(f[4 % EPV], f[5 % EPV], f[6 % EPV], f[7 % EPV]);
+          *reinterpret_cast<uint2*>(qr + (int64_t)vi * 8) = o;
+        } else {
+          *reinterpret_cast<uint32_t*>(qr + (int64_t)vi * 4) = pack4(f[0], f[1], f[2], f[3]);
+        }
+      }
+    }
+  };
+  if (rq.path == 0) emit(std::integral_constant<int, 0>{});
+  else if (rq.path == 1) emit(std::integral_constant<int, 1>{});
+  else emit(std::integral_constant<int, 2>{});
+}
+
+// ---- generic kernel: any K / stride / alignment, optional transposed output --------
+template <typename T> __device__ __forceinline__ float load_as_float(const T* p);
+template <> __device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int64_t ldx,
+                             int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
+                             int transpose, int scale_mode, float eps) {
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * ldx;
+  float amax = 0.f;
+  for (int64_t k = threadIdx.x; k < K; k += 256) amax = fmaxf(amax, fabsf(load_as_float<T>(xr + k)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) amax = fmaxf(amax, red[w]);
+  const RowQ rq = make_rowq(amax, scale_mode, eps);
+  if (threadIdx.x == 0) s_out[row] = rq.s;
+  for (int64_t k = threadIdx.x; k < K; k += 256) {
+    const float xv = load_as_float<T>(xr + k);
+    float m;
+    if (rq.path == 0) m = quant_fast(xv, rq);
+    else if (rq.path == 1) m = quant_div(xv, rq);
+    else m = quant_mul(xv, rq);
+    if (transpose) xq[k * ldq + row] = code_of(m);
+    else xq[row * ldq + k] = code_of(m);
+  }
+}
+
+// ---- transposed output, tiled: 32 rows per CTA, coalesced both ways ----------------
+// Pass 1 computes the 32 row scales (one warp per 4 rows); pass 2 re-reads the rows
+// (L2 hits: 32 rows were just streamed by this CTA), quantises 32x128 tiles into
+// shared memory and writes them out as 128 runs of 32 contiguous bytes.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, int64_t ldx,
+                                int8_t* __restrict__ xq_t, int64_t ldq,
+                                float* __restrict__ s_out, int scale_mode, float eps) {
+  __shared__ RowQ rowq[32];
+  __shared__ int8_t tile[128][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * 32;
+  for (int r = warp; r < 32; r += 8) {
+    const int64_t row = row0 + r;
+    float amax = 0.f;
+    if (row < M) {
+      const T* xr = x + row * ldx;
+      for (int64_t k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(load_as_float<T>(xr + k)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) {
+      const RowQ rq = make_rowq(amax, scale_mode, eps);
+      rowq[r] = rq;
+      if (row < M) s_out[row] = rq.s;
+    }
+  }
+  __syncthreads();
+  for (int64_t k0 = 0; k0 < K; k0 += 128) {
+    // quantise: thread (r = tid/8, c4 = tid%8) handles 16 consecutive k of row r
+    {
+      const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 16;
+      const int64_t row = row0 + r;
+      const RowQ rq = rowq[r];
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        const int64_t k = k0 + c0 + j;
+        int8_t code = 0;
+        if (row < M && k < K) {
+          const float xv = load_as_float<T>(x + row * ldx + k);
+          float m;
+          if (rq.path == 0) m = quant_fast(xv, rq);
+          else if (rq.path == 1) m = quant_div(xv, rq);
+          else m = quant_mul(xv, rq);
+          code = code_of(m);
+        }
+        tile[c0 + j][r] = code;
+      }
+    }
+    __syncthreads();
+    // write: 128 k-rows x 32 bytes; thread -> (k = tid/2 , half = tid%2) 16 bytes
+    {
+      const int kk = threadIdx.x >> 1, h = (threadIdx.x & 1) * 16;
+      const int64_t k = k0 + kk;
+      if (k < K) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t row = row0 + h + j;
+          if (row < M) xq_t[k * ldq + row] = tile[kk][h + j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int TPR, int VPT>
+int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int64_t ldq,
+               float* s, const pq_quant_spec& spec, cudaStream_t st) {
+  constexpr int THREADS = (TPR > 256 ? TPR : 256);
+  constexpr int ROWS = THREADS / TPR;
+  const int64_t grid = (M + ROWS - 1) / ROWS;
+  rowwise_quant_vec_kernel<T, TPR, VPT><<<(unsigned)grid, THREADS, 0, st>>>(
+      (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  PQ_CUDA(cudaGetLastError());
+  return PQ_OK;
+}
+
+template <typename T>
+int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq,
+             float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  if (M == 0) return PQ_OK;
+  if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
+  if (transpose) {
+    const int64_t grid = (M + 31) / 32;
+    rowwise_quant_transposed_kernel<T><<<(unsigned)grid, 256, 0, st>>>(
+        (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    PQ_CUDA(cudaGetLastError());
+    return PQ_OK;
+  }
+  const bool vec_ok = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) &&
+                      ((ldx * (int64_t)sizeof(T)) % 16 == 0) &&
+                      (((uintptr_t)xq % EPV) == 0) && (ldq % EPV == 0) &&
+                      (K / EPV <= 8192);
+  if (!vec_ok) {
+    rowwise_quant_generic_kernel<T><<<(unsigned)M, 256, 0, st>>>(
+        (const T*)x, M, K, ldx, xq, ldq, s, 0, spec.scale_mode, spec.eps);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    PQ_CUDA(cudaGetLastError());
+    return PQ_OK;
+  }
+  const int nvec = (int)(K / EPV);
+#define PQ_LAUNCH(TPR, VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st)
+  if (nvec <= 32 * 4) PQ_LAUNCH(32, 4);
+  if (nvec <= 64 * 4) PQ_LAUNCH(64, 4);
+  if (nvec <= 128 * 4) PQ_LAUNCH(128, 4);
+  if (nvec <= 256 * 4) PQ_LAUNCH(256, 4);
+  if (nvec <= 512 * 4) PQ_LAUNCH(512, 4);
+  if (nvec <= 1024 * 4) PQ_LAUNCH(1024, 4);
+  PQ_LAUNCH(1024, 8);
+#undef PQ_LAUNCH
+}
+
+}  // namespace
+
+int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
+                         int8_t* xq, int64_t ldq, float* s, int transpose,
+                         const pq_quant_spec& spec, cudaStream_t stream) {
+  if (M < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: bad shape M=%lld K=%lld", (long long)M, (long long)K);
+  if (M > 0 && (!x || !xq || !s)) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: null pointer");
+  if (ldx < K) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: ldx=%lld < K=%lld", (long long)ldx, (long long)K);
+  if (!transpose && ldq < K) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: ldq=%lld < K=%lld", (long long)ldq, (long long)K);
+  if (transpose && ldq < M) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: transposed ldq=%lld < M=%lld", (long long)ldq, (long long)M);
+  if (spec.scale_mode < PQ_DIV || spec.scale_mode > PQ_INV_SCALE)
+    PQ_FAIL(PQ_ERR_ARG, "rowwise quant: bad scale_mode %d", spec.scale_mode);
+  if (spec.qmin != -128 && spec.qmin != -127)
+    PQ_FAIL(PQ_ERR_ARG, "rowwise quant: qmin must be -128 or -127");
+  switch (x_dtype) {
+    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream);
+    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream);
+    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream);
+    default: PQ_FAIL(PQ_ERR_ARG, "rowwise quant: unsupported dtype %d", x_dtype);
+  }
+}
+
+}  // namespace pq

@@ -1,0 +1,187 @@
+"""Functional API of the dynamic-quantized linear path.
+
+Every function takes CUDA tensors, enqueues on the current CUDA stream and never
+synchronises.  CPU tensors raise: there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import PQ_BF16, PQ_F16, PQ_F32, PQQuantSpec
+
+_DT = {torch.float32: PQ_F32, torch.float16: PQ_F16, torch.bfloat16: PQ_BF16}
+
+
+@dataclasses.dataclass(frozen=True)
+class QuantSpec:
+    """Scale-computation knobs.  Default == SPEC v0 (true division, no eps)."""
+    scale_mode: int = _lib.PQ_DIV
+    eps: float = 0.0
+    qmin: int = -128
+
+    def c(self) -> PQQuantSpec:
+        return PQQuantSpec(self.scale_mode, self.eps, self.qmin)
+
+
+DEFAULT_SPEC = QuantSpec()
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.ProtoquantError(f"{name} must be a CUDA tensor: protoquant_b200 has no CPU fallback")
+
+
+def _pad16(k: int) -> int:
+    return (k + 15) // 16 * 16
+
+
+def _specp(spec: Optional[QuantSpec]):
+    return ctypes.byref((spec or DEFAULT_SPEC).c())
+
+
+def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(x.shape)}")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    return x
+
+
+def alloc_q(rows: int, cols: int, device) -> torch.Tensor:
+    """int8 [rows, cols] whose row stride is padded to a multiple of 16 bytes (TMA requirement)."""
+    buf = torch.empty((rows, _pad16(cols)), dtype=torch.int8, device=device)
+    return buf[:, :cols]
+
+
+def quantize_act(x: torch.Tensor, transpose: bool = False, spec: Optional[QuantSpec] = None,
+                 out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-token int8 quantisation of x [M,K] -> (xq int8 [M,K] (or [K,M] if transpose), s_x fp32 [M])."""
+    _require_cuda(x, "x")
+    x = _rows2d(x)
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported activation dtype {x.dtype}")
+    M, K = x.shape
+    if out is None:
+        xq = alloc_q(K, M, x.device) if transpose else alloc_q(M, K, x.device)
+        s = torch.empty((M,), dtype=torch.float32, device=x.device)
+    else:
+        xq, s = out
+    if M == 0:
+        return xq, s
+    rc = _lib.lib().pq_act_quant(x.data_ptr(), _DT[x.dtype], M, K, x.stride(0), xq.data_ptr(), xq.stride(0),
+                                 s.data_ptr(), int(transpose), _specp(spec), _stream())
+    _lib.check(rc, "pq_act_quant")
+    return xq, s
+
+
+def quantize_weight(w: torch.Tensor, spec: Optional[QuantSpec] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-output-channel int8 quantisation of W [N,K] -> (Wq int8 [N,K], s_w fp32 [N])."""
+    _require_cuda(w, "w")
+    w = _rows2d(w)
+    if w.dtype not in _DT:
+        raise TypeError(f"unsupported weight dtype {w.dtype}")
+    N, K = w.shape
+    wq = alloc_q(N, K, w.device)
+    s = torch.empty((N,), dtype=torch.float32, device=w.device)
+    if N:
+        rc = _lib.lib().pq_weight_quant(w.data_ptr(), _DT[w.dtype], N, K, w.stride(0), wq.data_ptr(), wq.stride(0),
+                                        s.data_ptr(), _specp(spec), _stream())
+        _lib.check(rc, "pq_weight_quant")
+    return wq, s
+
+
+def _gemm_operand(t: torch.Tensor, name: str) -> torch.Tensor:
+    _require_cuda(t, name)
+    if t.dtype != torch.int8 or t.dim() != 2:
+        raise TypeError(f"{name} must be a 2-D int8 tensor")
+    if t.stride(1) != 1 or t.stride(0) % 16 or t.data_ptr() % 16:
+        p = alloc_q(t.shape[0], t.shape[1], t.device)
+        p.copy_(t)
+        t = p
+    return t
+
+
+def qgemm_i32(xq: torch.Tensor, wq: torch.Tensor) -> torch.Tensor:
+    """Exact int32 accumulators acc[M,N] = xq[M,K] . wq[N,K]^T (parity hook)."""
+    xq = _gemm_operand(xq, "xq")
+    wq = _gemm_operand(wq, "wq")
+    M, K = xq.shape
+    N = wq.shape[0]
+    if wq.shape[1] != K:
+        raise ValueError("K mismatch")
+    acc = torch.empty((M, N), dtype=torch.int32, device=xq.device)
+    if M and N:
+        rc = _lib.lib().pq_qgemm_i32(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), acc.data_ptr(), N,
+                                     M, N, K, _stream())
+        _lib.check(rc, "pq_qgemm_i32")
+    return acc
+
+
+def qgemm(xq: torch.Tensor, s_x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tensor,
+          bias: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[M,N] = cast((float(xq.wq^T) * s_x[m]) * s_w[n] + bias[n])."""
+    xq = _gemm_operand(xq, "xq")
+    wq = _gemm_operand(wq, "wq")
+    M, K = xq.shape
+    N = wq.shape[0]
+    if wq.shape[1] != K:
+        raise ValueError("K mismatch")
+    if out_dtype not in _DT:
+        raise TypeError(f"unsupported output dtype {out_dtype}")
+    for t, n, ln in ((s_x, "s_x", M), (s_w, "s_w", N)):
+        _require_cuda(t, n)
+        if t.dtype != torch.float32 or t.numel() != ln or not t.is_contiguous():
+            raise TypeError(f"{n} must be a contiguous fp32 tensor of {ln} elements")
+    if bias is not None:
+        _require_cuda(bias, "bias")
+        if bias.dtype != torch.float32 or not bias.is_contiguous():
+            bias = bias.to(torch.float32).contiguous()
+        if bias.numel() != N:
+            raise ValueError("bias size mismatch")
+    y = out if out is not None else torch.empty((M, N), dtype=out_dtype, device=xq.device)
+    if M and N:
+        rc = _lib.lib().pq_qgemm(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), s_x.data_ptr(),
+                                 s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                 y.data_ptr(), _DT[y.dtype], y.stride(0), M, N, K, _stream())
+        _lib.check(rc, "pq_qgemm")
+    return y
+
+
+def qlinear(x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None, spec: Optional[QuantSpec] = None) -> torch.Tensor:
+    """Dynamic-quant linear forward: x[...,K] -> y[...,N] with cached (wq, s_w)."""
+    _require_cuda(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    xq, s_x = quantize_act(x2, spec=spec)
+    y = qgemm(xq, s_x, wq, s_w, bias, out_dtype or x.dtype)
+    return y.reshape(*lead, wq.shape[0])
+
+
+def dequantize(q: torch.Tensor, s: torch.Tensor, axis: int = 0, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """out[r,c] = q[r,c] * s[r] (axis=0) or q[r,c] * s[c] (axis=1)."""
+    _require_cuda(q, "q")
+    _require_cuda(s, "s")
+    if q.dim() != 2 or q.dtype != torch.int8:
+        raise TypeError("q must be a 2-D int8 tensor")
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    rows, cols = q.shape
+    if s.dtype != torch.float32 or not s.is_contiguous() or s.numel() != (rows if axis == 0 else cols):
+        raise TypeError("s must be contiguous fp32 with one entry per slice along `axis`")
+    out = torch.empty((rows, cols), dtype=out_dtype, device=q.device)
+    if rows and cols:
+        rc = _lib.lib().pq_dequant(q.data_ptr(), q.stride(0), s.data_ptr(), axis, out.data_ptr(), _DT[out_dtype],
+                                   out.stride(0), rows, cols, _stream())
+        _lib.check(rc, "pq_dequant")
+    return out

@@ -1,0 +1,74 @@
+"""Drop-in replacement for nn.Linear on the dynamic int8 path.
+
+forward:  x[...,K] --per-token int8--> xq,s_x --tcgen05 int8 GEMM + fused dequant--> y[...,N]
+Weights are quantised once, per output channel, when the module is built.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import functional as F
+
+
+class DynamicQuantLinear(nn.Module):
+    """int8 weight (per-output-channel scale) + dynamic per-token int8 activations."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None,
+                 out_dtype: Optional[torch.dtype] = None, spec: Optional[F.QuantSpec] = None):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.out_dtype = out_dtype
+        self.spec = spec
+        kp = (in_features + 15) // 16 * 16
+        self.register_buffer("qweight_storage", torch.zeros((out_features, kp), dtype=torch.int8, device=device))
+        self.register_buffer("weight_scale", torch.ones((out_features,), dtype=torch.float32, device=device))
+        if bias:
+            self.register_buffer("bias", torch.zeros((out_features,), dtype=torch.float32, device=device))
+        else:
+            self.bias = None
+
+    @property
+    def qweight(self) -> torch.Tensor:
+        """int8 [N, K] view whose row stride is a multiple of 16 bytes."""
+        return self.qweight_storage[:, : self.in_features]
+
+    @classmethod
+    def from_float(cls, linear: nn.Linear, out_dtype: Optional[torch.dtype] = None,
+                   spec: Optional[F.QuantSpec] = None) -> "DynamicQuantLinear":
+        w = linear.weight.detach()
+        if not w.is_cuda:
+            raise RuntimeError("DynamicQuantLinear.from_float needs the nn.Linear on a CUDA device "
+                               "(weights are quantised by the GPU kernel; there is no CPU path)")
+        m = cls(linear.in_features, linear.out_features, linear.bias is not None, device=w.device,
+                out_dtype=out_dtype, spec=spec)
+        wq, s = F.quantize_weight(w, spec=spec)
+        m.qweight_storage[:, : linear.in_features].copy_(wq)
+        m.weight_scale.copy_(s)
+        if linear.bias is not None:
+            m.bias.copy_(linear.bias.detach().to(torch.float32))
+        return m
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F.qlinear(x, self.qweight, self.weight_scale, self.bias, self.out_dtype or x.dtype, self.spec)
+
+    def dequantized_weight(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        return F.dequantize(self.qweight, self.weight_scale, axis=0, out_dtype=dtype)
+
+    def extra_repr(self) -> str:
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, int8"
+
+
+def swap_linear(model: nn.Module, min_features: int = 0, out_dtype: Optional[torch.dtype] = None,
+                spec: Optional[F.QuantSpec] = None, skip=()) -> nn.Module:
+    """Replace every nn.Linear (in/out features >= min_features, name not in `skip`) in place."""
+    for name, child in list(model.named_children()):
+        if isinstance(child, nn.Linear) and name not in skip and \
+                min(child.in_features, child.out_features) >= min_features:
+            setattr(model, name, DynamicQuantLinear.from_float(child, out_dtype=out_dtype, spec=spec))
+        else:
+            swap_linear(child, min_features, out_dtype, spec, skip)
+    return model

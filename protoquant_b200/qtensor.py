@@ -1,0 +1,73 @@
+"""QTensor: int8 payload + fp32 scales + quantisation axis.
+
+The reference's real class is unavailable (REFERENCE ABSENT); this keeps the
+"QTensor-style quantize/dequantize" surface BASELINE.json names.  Names the reference may
+use are collected in compat.py.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import functional as F
+
+
+class QTensor:
+    """A row-wise (axis=-1 reduced) symmetric int8 quantised 2-D tensor.
+
+    ``data``  int8  [R, C]  (row stride padded to 16 bytes so it can feed the GEMM directly)
+    ``scale`` fp32  [R]     one scale per row: per token for activations, per output channel
+                            for weights W[N,K]
+    ``axis``  the reduced axis of the original tensor (always the last one, -1)
+    """
+
+    __slots__ = ("data", "scale", "axis", "orig_dtype", "orig_shape")
+
+    def __init__(self, data: torch.Tensor, scale: torch.Tensor, axis: int = -1,
+                 orig_dtype: torch.dtype = torch.float32, orig_shape=None):
+        self.data = data
+        self.scale = scale
+        self.axis = axis
+        self.orig_dtype = orig_dtype
+        self.orig_shape = tuple(orig_shape) if orig_shape is not None else tuple(data.shape)
+
+    @property
+    def shape(self):
+        return self.orig_shape
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def dequantize(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        out = F.dequantize(self.data, self.scale, axis=0, out_dtype=dtype or self.orig_dtype)
+        return out.reshape(self.orig_shape)
+
+    def int_repr(self) -> torch.Tensor:
+        return self.data
+
+    def state(self):
+        return {"data": self.data.contiguous(), "scale": self.scale, "axis": self.axis,
+                "orig_dtype": self.orig_dtype, "orig_shape": self.orig_shape}
+
+    def __repr__(self):
+        return (f"QTensor(shape={self.orig_shape}, dtype=int8, scale=fp32[{self.scale.numel()}], "
+                f"axis={self.axis}, orig_dtype={self.orig_dtype}, device={self.data.device})")
+
+
+def quantize(t: torch.Tensor, axis: int = -1, spec: Optional[F.QuantSpec] = None) -> QTensor:
+    """Symmetric int8 quantisation with one scale per slice along the last axis.
+
+    ``t`` [..., C] is flattened to [R, C]; each row gets ``scale = absmax/127`` and
+    ``q = rne(t / scale)``.  Only ``axis=-1`` (reduce over the last dim) is supported,
+    which covers both per-token activations and per-output-channel weights W[N,K]."""
+    if axis not in (-1, t.dim() - 1):
+        raise NotImplementedError("QTensor quantisation reduces over the last axis only")
+    t2 = t.reshape(-1, t.shape[-1])
+    q, s = F.quantize_act(t2, spec=spec)
+    return QTensor(q, s, axis=-1, orig_dtype=t.dtype, orig_shape=t.shape)
+
+
+def dequantize(qt: QTensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    return qt.dequantize(dtype)

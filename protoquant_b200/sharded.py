@@ -1,0 +1,96 @@
+"""Column-parallel dynamic-quant linear (BASELINE.json north_star (4)).
+
+Rank r of a G-rank group holds rows [r*N/G, (r+1)*N/G) of (Wq, s_w, bias).  The activation
+is replicated; every rank quantises it (cheap, HBM-bound), runs the int8 GEMM on its weight
+slice and the output slices are all-gathered along N over NCCL/NVLink.  Column sharding does
+not change any accumulation order, so the gathered result is bit-identical to the 1-GPU one.
+
+The gather is the path's only exchange step.  `min_out_features` implements the north
+star's "used only for layers big enough to benefit": smaller layers stay replicated.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import functional as F
+
+
+def shard_bounds(n: int, world: int, rank: int, align: int = 8):
+    """[lo, hi) of rank's slice of n output channels; slices are `align`-aligned except the last."""
+    per = (n + world - 1) // world
+    per = (per + align - 1) // align * align
+    lo = min(rank * per, n)
+    hi = min(lo + per, n)
+    return lo, hi
+
+
+class ShardedDynamicQuantLinear(nn.Module):
+    def __init__(self, qweight_full: torch.Tensor, weight_scale_full: torch.Tensor,
+                 bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,
+                 spec: Optional[F.QuantSpec] = None,
+                 local_forward: Optional[Callable] = None):
+        """qweight_full [N,K] int8, weight_scale_full [N] fp32, bias_full [N] fp32|None: the
+        UNSHARDED quantised weight (every rank passes the same tensors; each keeps its slice).
+        `local_forward(x2d, wq, s_w, bias, out_dtype)` defaults to the CUDA path; tests on a
+        CPU-only box inject the oracle there to exercise the shard/gather logic over gloo."""
+        super().__init__()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.out_features, self.in_features = qweight_full.shape
+        self.out_dtype = out_dtype
+        self.spec = spec
+        self._local_forward = local_forward
+        per = shard_bounds(self.out_features, self.world, 0)[1]
+        self.per = per
+        lo, hi = shard_bounds(self.out_features, self.world, self.rank)
+        self.lo, self.hi = lo, hi
+        dev = qweight_full.device
+        kp = (self.in_features + 15) // 16 * 16
+        # every rank allocates the same padded slice height so the all-gather is regular
+        wq = torch.zeros((per, kp), dtype=torch.int8, device=dev)
+        sw = torch.ones((per,), dtype=torch.float32, device=dev)
+        wq[: hi - lo, : self.in_features].copy_(qweight_full[lo:hi])
+        sw[: hi - lo].copy_(weight_scale_full[lo:hi])
+        self.register_buffer("qweight_storage", wq)
+        self.register_buffer("weight_scale", sw)
+        if bias_full is not None:
+            b = torch.zeros((per,), dtype=torch.float32, device=dev)
+            b[: hi - lo].copy_(bias_full[lo:hi].to(torch.float32))
+            self.register_buffer("bias", b)
+        else:
+            self.bias = None
+
+    @property
+    def qweight(self):
+        return self.qweight_storage[:, : self.in_features]
+
+    def local(self, x2: torch.Tensor, out_dtype) -> torch.Tensor:
+        if self._local_forward is not None:
+            return self._local_forward(x2, self.qweight, self.weight_scale, self.bias, out_dtype)
+        return F.qlinear(x2, self.qweight, self.weight_scale, self.bias, out_dtype, self.spec)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        out_dtype = self.out_dtype or x.dtype
+        y_local = self.local(x2, out_dtype).contiguous()          # [M, per]
+        if self.world == 1:
+            return y_local[:, : self.out_features].reshape(*lead, self.out_features)
+        M = y_local.shape[0]
+        gathered = torch.empty((self.world, M, self.per), dtype=y_local.dtype, device=y_local.device)
+        dist.all_gather_into_tensor(gathered, y_local, group=self.group)
+        y = gathered.permute(1, 0, 2).reshape(M, self.world * self.per)[:, : self.out_features]
+        return y.reshape(*lead, self.out_features)
+
+
+def maybe_shard(linear_q, group=None, min_out_features: int = 16384, **kw):
+    """Shard a DynamicQuantLinear across `group` only if it is big enough to benefit."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or linear_q.out_features < min_out_features:
+        return linear_q
+    return ShardedDynamicQuantLinear(linear_q.qweight, linear_q.weight_scale, linear_q.bias, group=group,
+                                     out_dtype=linear_q.out_dtype, spec=linear_q.spec, **kw)
