@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""Benchmark of the dynamic-quantized int8 linear path (BASELINE.json `metric`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "llama7b_linears_2048tok", BASELINE.json configs[2]): one "step"
+pushes one batch of 2048 synthetic bf16 tokens through the seven linears of a Llama-7B block
+(q,k,v,o: 4096->4096; gate,up: 4096->11008; down: 11008->4096), each as a dynamic-quant linear
+forward = per-token act-quant kernel + tcgen05 int8 GEMM with the fused dequant epilogue
+(14 kernel launches / step, random-init weights quantised once at load).
+
+  value   whole-job int8 TOPS = n_gpus * 2*M*sum(N*K) / step time, inputs resident in HBM.
+  e2e     same metric with HOST buffers: every step copies the four activation tensors from
+          pinned host memory and brings the seven outputs back (copies inside the timed region).
+  N > 1   rows (tokens) are independent, so the path shards by tokens with no collective: every
+          rank runs the same step on its own 2048-token batch (weak scaling).  The column-
+          parallel Llama-70B linear with its NCCL all-gather (the path's one exchange step)
+          is timed beside it and reported under "sharded_70b".
+  --impl reference   times the oracle's CPU path (the reference checkout is absent, so the
+          restatement stands in: oracle/protoquant_oracle.py) on all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_TOKENS = 2048
+LINEARS = [  # name, K (in), N (out), which activation buffer feeds it
+    ("q_proj", 4096, 4096, "x_attn"), ("k_proj", 4096, 4096, "x_attn"), ("v_proj", 4096, 4096, "x_attn"),
+    ("o_proj", 4096, 4096, "attn_out"), ("gate_proj", 4096, 11008, "x_mlp"), ("up_proj", 4096, 11008, "x_mlp"),
+    ("down_proj", 11008, 4096, "h_mlp"),
+]
+ACTS = {"x_attn": 4096, "attn_out": 4096, "x_mlp": 4096, "h_mlp": 11008}
+OPS_PER_STEP = sum(2 * M_TOKENS * n * k for _, k, n, _ in LINEARS)
+NOMINAL_INT8_TOPS = 4500.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.stop_flag = threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+        for bit, n in names.items():
+            if r & bit:
+                self.reasons.add(n)
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.sample()
+            except Exception:
+                break
+            time.sleep(self.period)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU baseline arm: the oracle's torch-threaded restatement of the same step (kind = "port":
+    /root/reference holds no sources to compile or import)."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import protoquant_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    # bounded sample: the full 7-linear step on a 256-token slice of the 2048-token batch
+    m_sample = 256
+    layers = []
+    for name, k, n, src in LINEARS:
+        w = (torch.rand(n, k) * 2 - 1) / k ** 0.5
+        wq, sw = O.quantize_rowwise(w)
+        layers.append((torch.from_numpy(wq).t(), torch.from_numpy(sw), torch.randn(n), src))
+    acts = {a: torch.randn(m_sample, k).to(torch.bfloat16) for a, k in ACTS.items()}
+
+    def step():
+        for wq_t, sw, b, src in layers:
+            O.qlinear_torch_cpu(acts[src], wq_t, sw, b, torch.bfloat16)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    ops = OPS_PER_STEP * m_sample / M_TOKENS
+    tops = ops / dt / 1e12
+    sample = f"{m_sample}-token slice of the 2048-token step, all 7 linears, {steps} steps"
+    line = {
+        "impl": "reference", "metric": "int8_qlinear_tops", "value": tops, "unit": "TOPS", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": {"workload": "llama7b_linears_2048tok", "tokens": m_sample, "linears": [l[0] for l in LINEARS]},
+        "tokens_per_s": m_sample / dt,
+        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(budget_s=12.0):
+    """Same oracle path, timed beside the GPU numbers on rank 0 (bounded sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import protoquant_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m_sample = 256
+    g = torch.Generator().manual_seed(0)
+    layers = []
+    for name, k, n, src in LINEARS:
+        wq = torch.randint(-127, 128, (n, k), dtype=torch.int8, generator=g)
+        layers.append((wq.t(), torch.rand(n, generator=g) * 1e-3, torch.randn(n, generator=g), src))
+    acts = {a: torch.randn(m_sample, k, generator=g).to(torch.bfloat16) for a, k in ACTS.items()}
+
+    def step():
+        for wq_t, sw, b, src in layers:
+            O.qlinear_torch_cpu(acts[src], wq_t, sw, b, torch.bfloat16)
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 20:
+            break
+    dt = (time.perf_counter() - t0) / n
+    tops = OPS_PER_STEP * m_sample / M_TOKENS / dt / 1e12
+    return {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port",
+            "sample": f"{m_sample}-token slice of the 2048-token step, all 7 linears, {n} steps, torch CPU _int_mm",
+            "tokens_per_s": m_sample / dt}
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import protoquant_b200 as pq
+    from protoquant_b200 import functional as F
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; protoquant_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    torch.manual_seed(1234 + rank)
+
+    # ---- load-time: random-init weights of the named architecture, quantised once ----
+    mods = {}
+    for name, k, n, src in LINEARS:
+        lin = torch.nn.Linear(k, n, bias=True).to(torch.bfloat16).to(dev)
+        mods[name] = pq.DynamicQuantLinear.from_float(lin)
+        del lin
+    acts = {a: torch.randn(M_TOKENS, k, device=dev).to(torch.bfloat16) for a, k in ACTS.items()}
+    xq_ws = {a: (F.alloc_q(M_TOKENS, k, dev), torch.empty(M_TOKENS, dtype=torch.float32, device=dev)) for a, k in ACTS.items()}
+    outs = {name: torch.empty(M_TOKENS, n, dtype=torch.bfloat16, device=dev) for name, k, n, _ in LINEARS}
+
+    def linear_fwd(name, src):
+        m = mods[name]
+        xq, sx = F.quantize_act(acts[src], out=xq_ws[src])
+        F.qgemm(xq, sx, m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
+
+    def step():
+        for name, k, n, src in LINEARS:
+            linear_fwd(name, src)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = pq.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = pq.launch_count() - launches0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    if not sampler.samples and sampler.nv is not None:
+        # region too short to be sampled: take samples under the same load right now
+        for _ in range(200):
+            step()
+        try:
+            sampler.sample()
+        except Exception:
+            pass
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = world * OPS_PER_STEP / (ms_per_step * 1e-3) / 1e12
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events on the launch stream ----
+    gemm_ms, quant_ms = 0.0, 0.0
+    evs = []
+    roof_steps = min(args.steps, 50)
+    for _ in range(roof_steps):
+        for name, k, n, src in LINEARS:
+            m = mods[name]
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            xq, sx = F.quantize_act(acts[src], out=xq_ws[src])
+            b.record()
+            F.qgemm(xq, sx, m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
+            c.record()
+            evs.append((a, b, c, k, n))
+    torch.cuda.synchronize()
+    quant_bytes = 0
+    for a, b, c, k, n in evs:
+        quant_ms += a.elapsed_time(b)
+        gemm_ms += b.elapsed_time(c)
+        quant_bytes += M_TOKENS * (3 * k + 4)
+    gemm_tops = OPS_PER_STEP * roof_steps / (gemm_ms * 1e-3) / 1e12
+    peak_tops = 2.0 * peaks["bf16_tflops"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("qgemm_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "qgemm_kernel (tcgen05.mma.kind::i8)", "achieved": gemm_tops, "peak": peak_tops,
+        "unit": "TFLOP/s", "frac": gemm_tops / peak_tops, "traffic": traffic,
+        "peak_note": f"2 x {peaks['source']} cuBLAS bf16 burst {peaks['bf16_tflops']} TF/s (int8 tensor rate = 2x bf16); "
+                     f"nominal dense int8 {NOMINAL_INT8_TOPS:.0f} TOPS -> frac_of_nominal {gemm_tops / NOMINAL_INT8_TOPS:.3f}",
+        "avg_launch_ms": gemm_ms / (roof_steps * len(LINEARS)),
+        "act_quant": {"bound": "hbm", "achieved": quant_bytes / (quant_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                      "unit": "GB/s", "frac": quant_bytes / (quant_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "note": "config-size inputs (16-45 MB) are L2-resident and launch-latency bound; see act_quant_stream"},
+    }
+    # HBM-streaming point for the activation quantizer (traffic >> L2): SURVEY.md §8d
+    if rank == 0:
+        Mbig, Kbig = 131072, 4096
+        xb = torch.randn(Mbig, Kbig, device=dev).to(torch.bfloat16)
+        qb, sb = F.alloc_q(Mbig, Kbig, dev), torch.empty(Mbig, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            F.quantize_act(xb, out=(qb, sb))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(10):
+            F.quantize_act(xb, out=(qb, sb))
+        s1.record()
+        torch.cuda.synchronize()
+        gbs = 10 * Mbig * (3 * Kbig + 4) / (s0.elapsed_time(s1) * 1e-3) / 1e9
+        roofline["act_quant_stream"] = {"bound": "hbm", "shape": [Mbig, Kbig], "dtype": "bf16", "achieved": gbs,
+                                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+        del xb, qb, sb
+
+    # ---- e2e: host buffers, copies inside the timed region, through the public module API ----
+    host_in = {a: torch.randn(M_TOKENS, k).to(torch.bfloat16).pin_memory() for a, k in ACTS.items()}
+    host_out = {name: torch.empty(M_TOKENS, n, dtype=torch.bfloat16).pin_memory() for name, k, n, _ in LINEARS}
+    h2d_bytes = sum(t.numel() * 2 for t in host_in.values())
+    d2h_bytes = sum(t.numel() * 2 for t in host_out.values())
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+
+    def e2e_step():
+        ready = {}
+        with torch.cuda.stream(copy_in):
+            for a in ACTS:
+                acts[a].copy_(host_in[a], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_in)
+                ready[a] = ev
+        for name, k, n, src in LINEARS:
+            main.wait_event(ready[src])
+            y = mods[name](acts[src])                      # public API: the nn.Linear replacement
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(done)
+                host_out[name].copy_(y, non_blocking=True)
+                y.record_stream(copy_out)
+        main.wait_stream(copy_out)
+        copy_in.wait_stream(main)
+
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_ms_step = e2e_ms / e2e_steps
+    e2e = {"value": world * OPS_PER_STEP / (e2e_ms_step * 1e-3) / 1e12, "unit": "TOPS", "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_step, "steps": e2e_steps,
+           "tokens_per_s": world * M_TOKENS / (e2e_ms_step * 1e-3)}
+
+    # ---- column-parallel Llama-70B linear with its all-gather (the path's exchange step) ----
+    sharded = None
+    try:
+        sharded = sharded_leg(pq, torch, dist, dev, rank, world)
+    except Exception as ex:  # never let the side measurement kill the headline line
+        sharded = {"error": repr(ex)[:200]}
+
+    cpu = cpu_baseline_leg() if (rank == 0 and world == 1) else None
+    clocks = sampler.result()
+    if rank == 0:
+        line = {
+            "metric": "int8_qlinear_tops", "value": value, "unit": "TOPS", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "llama7b_linears_2048tok", "tokens_per_gpu": M_TOKENS, "act_dtype": "bf16",
+                       "out_dtype": "bf16", "linears": {l[0]: [l[1], l[2]] for l in LINEARS},
+                       "parallelism": f"tokens x{world} (no collective)",
+                       "l2": "inputs larger than L2: each step streams 202 MB of int8 weights + 0.27 GB of activations/outputs (> 126 MB L2)"},
+            "tokens_per_s": world * M_TOKENS / (ms_per_step * 1e-3),
+            "frac_of_nominal_int8": value / world / NOMINAL_INT8_TOPS,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "sharded_70b": sharded,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def sharded_leg(pq, torch, dist, dev, rank, world):
+    """Llama-70B up-projection (8192 -> 28672): replicated vs column-sharded + all-gather, M in {16, 2048}."""
+    K, N = 8192, 28672
+    g = torch.Generator(device=dev).manual_seed(7)
+    wq_full = torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev, generator=g)
+    sw_full = torch.rand(N, device=dev, generator=g) * 1e-3
+    res = {"layer": [K, N], "world": world}
+    full = pq.DynamicQuantLinear(K, N, bias=False, device=dev)
+    full.qweight_storage[:, :K].copy_(wq_full)
+    full.weight_scale.copy_(sw_full)
+    sh = pq.ShardedDynamicQuantLinear(wq_full, sw_full, None) if world > 1 else None
+    for M in (16, 2048):
+        x = torch.randn(M, K, device=dev, generator=g).to(torch.bfloat16)
+        for label, mod in (("replicated", full), ("sharded_allgather", sh)):
+            if mod is None:
+                continue
+            for _ in range(3):
+                mod(x)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                y = mod(x)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 20
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            res[f"M{M}_{label}"] = {"ms": ms, "tops": 2 * M * N * K / (ms * 1e-3) / 1e12, "tokens_per_s": M / (ms * 1e-3)}
+        if sh is not None:
+            res[f"M{M}_bit_identical"] = bool(torch.equal(sh(x), full(x)))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

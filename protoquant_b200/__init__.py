@@ -6,7 +6,7 @@ No Triton, no backend dispatch, no CPU fallback.
 from ._lib import ProtoquantError, launch_count, lib
 from .functional import (DEFAULT_SPEC, QuantSpec, dequantize as dequantize_tensor, qgemm, qgemm_i32, qlinear,
                          quantize_act, quantize_weight)
-from .qlinear import DynamicQuantLinear, swap_linear
+from .modules import DynamicQuantLinear, swap_linear
 from .qtensor import QTensor, dequantize, quantize
 from .sharded import ShardedDynamicQuantLinear, maybe_shard, shard_bounds
 

@@ -7,7 +7,7 @@ are PROVISIONAL guesses at common spellings, not citations.
 """
 from .functional import dequantize as dequantize_tensor
 from .functional import qgemm, qgemm_i32, qlinear, quantize_act, quantize_weight
-from .qlinear import DynamicQuantLinear, swap_linear
+from .modules import DynamicQuantLinear, swap_linear
 from .qtensor import QTensor, dequantize, quantize
 
 # provisional spellings

@@ -82,9 +82,9 @@ class ShardedDynamicQuantLinear(nn.Module):
         if self.world == 1:
             return y_local[:, : self.out_features].reshape(*lead, self.out_features)
         M = y_local.shape[0]
-        gathered = torch.empty((self.world, M, self.per), dtype=y_local.dtype, device=y_local.device)
+        gathered = torch.empty((self.world * M, self.per), dtype=y_local.dtype, device=y_local.device)
         dist.all_gather_into_tensor(gathered, y_local, group=self.group)
-        y = gathered.permute(1, 0, 2).reshape(M, self.world * self.per)[:, : self.out_features]
+        y = gathered.view(self.world, M, self.per).permute(1, 0, 2).reshape(M, self.world * self.per)[:, : self.out_features]
         return y.reshape(*lead, self.out_features)
 
 

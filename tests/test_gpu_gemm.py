@@ -1,0 +1,158 @@
+"""GPU parity tests of the tcgen05 int8 GEMM + fused dequant epilogue:
+int32 accumulators bit-exact against an exact CPU integer matmul for every tile configuration,
+epilogue bit-exact against the oracle's fp32 operation sequence, and within the stated bf16/fp16
+tolerance of the un-quantised float linear."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+import protoquant_b200 as pq
+import protoquant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [-1, 0, 1, 2, 3, 4]   # -1 = heuristic; see launch_typed() in csrc/qgemm_tcgen05.cu
+
+
+@pytest.fixture(autouse=True)
+def _reset_cfg():
+    yield
+    pq.lib().pq_debug_set_gemm_config(-1)
+
+
+def rand_i8(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-128, 128, shape, dtype=torch.int8, generator=g)
+
+
+def cpu_int_mm(a, b):
+    return torch.from_numpy(O.int_mm(a.numpy(), b.numpy()))
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+@pytest.mark.parametrize("shape", [
+    (1, 8, 16), (1, 64, 16), (16, 4096, 4096), (17, 40, 144), (128, 256, 128), (129, 257, 130),
+    (256, 256, 256), (300, 520, 1040), (384, 768, 768), (255, 1000, 3072), (512, 3072, 768),
+])
+def test_int32_accumulators_bit_exact(cfg, shape):
+    M, N, K = shape
+    pq.lib().pq_debug_set_gemm_config(cfg)
+    a, b = rand_i8((M, K), 1), rand_i8((N, K), 2)
+    got = pq.qgemm_i32(a.cuda(), b.cuda())
+    assert torch.equal(got.cpu(), cpu_int_mm(a, b))
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 4])
+@pytest.mark.parametrize("shape", [(2048, 4096, 4096), (2048, 11008, 4096), (2048, 4096, 11008),
+                                   (4096, 3072, 768), (1024, 3584, 8192), (256, 8192, 28672)])
+def test_int32_full_size_shapes(cfg, shape):
+    """BASELINE.json configs: Llama-7B (4096/11008, 2048 tokens), BERT (768/3072, 4096 tokens),
+    Llama-70B column shard (28672/8 = 3584 out-channels, K=8192) and down-proj K=28672."""
+    M, N, K = shape
+    pq.lib().pq_debug_set_gemm_config(cfg)
+    a, b = rand_i8((M, K), 3), rand_i8((N, K), 4)
+    got = pq.qgemm_i32(a.cuda(), b.cuda())
+    assert torch.equal(got.cpu(), cpu_int_mm(a, b))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "int_mm_*.npz"))))
+@pytest.mark.parametrize("cfg", [-1, 0, 1])
+def test_int32_committed_golden(path, cfg):
+    d = np.load(path)
+    pq.lib().pq_debug_set_gemm_config(cfg)
+    got = pq.qgemm_i32(torch.from_numpy(d["a"]).cuda(), torch.from_numpy(d["b"]).cuda())
+    assert np.array_equal(got.cpu().numpy(), d["acc"])
+
+
+def test_int32_properties_at_scale():
+    """Properties that need no CPU matmul: linearity in W and column-shard concatenation."""
+    M, N, K = 8192, 8192, 8192
+    a = rand_i8((M, K), 5).cuda()
+    b1 = torch.randint(-64, 64, (N, K), dtype=torch.int8, generator=torch.Generator().manual_seed(6)).cuda()
+    b2 = torch.randint(-64, 64, (N, K), dtype=torch.int8, generator=torch.Generator().manual_seed(7)).cuda()
+    full = pq.qgemm_i32(a, b1 + b2)
+    assert torch.equal(full, pq.qgemm_i32(a, b1) + pq.qgemm_i32(a, b2))
+    parts = [pq.qgemm_i32(a, (b1 + b2)[lo:lo + 1024]) for lo in range(0, N, 1024)]
+    assert torch.equal(full, torch.cat(parts, dim=1))
+    # spot-check 64 random rows against the exact CPU product
+    rows = torch.randperm(M, generator=torch.Generator().manual_seed(8))[:64]
+    ref = cpu_int_mm(a[rows.cuda()].cpu(), (b1 + b2).cpu())
+    assert torch.equal(full[rows.cuda()].cpu(), ref)
+
+
+def test_persistent_scheduler_many_tiles():
+    """More tiles than CTAs in both dimensions, ragged on every edge -> exercises ring/phase wrap."""
+    M, N, K = 1100, 5000, 400
+    a, b = rand_i8((M, K), 9), rand_i8((N, K), 10)
+    for cfg in (0, 1, 2, 3, 4):
+        pq.lib().pq_debug_set_gemm_config(cfg)
+        assert torch.equal(pq.qgemm_i32(a.cuda(), b.cuda()).cpu(), cpu_int_mm(a, b)), cfg
+
+
+def _bits(t):
+    return t.view(torch.int32 if t.dtype == torch.float32 else torch.int16)
+
+
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 3])
+@pytest.mark.parametrize("out", [(torch.bfloat16, "bf16"), (torch.float16, "f16"), (torch.float32, "f32")])
+@pytest.mark.parametrize("shape,use_bias", [((256, 512, 512), True), ((100, 264, 272), False),
+                                            ((16, 4096, 4096), True), ((700, 1000, 768), True)])
+def test_fused_epilogue_bit_exact_vs_oracle(cfg, out, shape, use_bias):
+    """y = cast(((float(acc)*s_x)*s_w)+bias): same fp32 op order as the oracle -> identical bits."""
+    M, N, K = shape
+    dt, name = out
+    pq.lib().pq_debug_set_gemm_config(cfg)
+    g = torch.Generator().manual_seed(11)
+    xq, wq = rand_i8((M, K), 12), rand_i8((N, K), 13)
+    s_x = torch.rand(M, generator=g) * 0.1 + 1e-3
+    s_w = torch.rand(N, generator=g) * 0.01 + 1e-4
+    bias = torch.randn(N, generator=g) if use_bias else None
+    y = pq.qgemm(xq.cuda(), s_x.cuda(), wq.cuda(), s_w.cuda(), bias.cuda() if use_bias else None, dt)
+    ref = O.cast_out(O.dequant_epilogue(O.int_mm(xq.numpy(), wq.numpy()), s_x.numpy(), s_w.numpy(),
+                                        bias.numpy() if use_bias else None), name)
+    assert torch.equal(_bits(y.cpu()), _bits(ref))
+
+
+@pytest.mark.parametrize("out_dtype,rtol", [(torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -10), (torch.float32, 1e-6)])
+@pytest.mark.parametrize("shape", [(16, 4096, 4096), (2048, 11008, 4096), (2048, 4096, 11008), (4096, 3072, 768)])
+def test_qlinear_within_tolerance_of_fp32_epilogue(out_dtype, rtol, shape):
+    """Stated tolerance: |y - y_fp32| <= rtol*|y_fp32| + 1e-3*max|y_fp32| where y_fp32 is the
+    oracle's fp32 epilogue before the cast.  (In fact the outputs are bit-identical to the cast oracle.)"""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    wq, sw = pq.quantize_weight(w.cuda())
+    y = pq.qlinear(x.cuda(), wq, sw, bias.cuda(), out_dtype)
+    wq_o, sw_o = O.quantize_weight(w)
+    xq_o, sx_o = O.quantize_rowwise(x)
+    y32 = torch.from_numpy(O.dequant_epilogue(O.int_mm(xq_o, wq_o), sx_o, sw_o, bias.numpy()))
+    err = (y.cpu().float() - y32).abs()
+    tol = rtol * y32.abs() + 1e-3 * y32.abs().max()
+    assert bool((err <= tol).all())
+    name = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[out_dtype]
+    assert torch.equal(_bits(y.cpu()), _bits(O.cast_out(y32.numpy(), name)))
+    # and the whole thing is a faithful int8 approximation of the float linear
+    ref = torch.nn.functional.linear(x.float(), w, bias)
+    assert (y.cpu().float() - ref).abs().max() < 0.05 * ref.abs().max()
+
+
+def test_unaligned_operands_are_repacked_by_python_and_rejected_by_c_abi():
+    a, b = rand_i8((40, 100), 15), rand_i8((24, 100), 16)      # K=100: row stride not a multiple of 16
+    got = pq.qgemm_i32(a.cuda(), b.cuda())
+    assert torch.equal(got.cpu(), cpu_int_mm(a, b))
+    lib = pq.lib()
+    ac, bc = a.cuda().contiguous(), b.cuda().contiguous()
+    acc = torch.empty(40, 24, dtype=torch.int32, device="cuda")
+    rc = lib.pq_qgemm_i32(ac.data_ptr(), 100, bc.data_ptr(), 100, acc.data_ptr(), 24, 40, 24, 100, None)
+    assert rc == 2 and b"16 bytes" in lib.pq_last_error()      # PQ_ERR_ALIGN
+
+
+def test_empty_gemm():
+    assert pq.qgemm_i32(torch.empty(0, 64, dtype=torch.int8, device="cuda"), rand_i8((8, 64), 1).cuda()).shape == (0, 8)

@@ -1,0 +1,109 @@
+"""GPU tests of the nn.Linear replacement, the swap helper, the host-buffer C API and the
+sharded module (single rank; multi-rank when the box has more than one GPU)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import ROOT
+import protoquant_b200 as pq
+import protoquant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(t):
+    return t.view(torch.int32 if t.dtype == torch.float32 else torch.int16)
+
+
+@pytest.mark.parametrize("dtype,name", [(torch.bfloat16, "bf16"), (torch.float16, "f16")])
+@pytest.mark.parametrize("features,tokens", [((4096, 4096), (16,)), ((768, 3072), (32, 128)), ((3072, 768), (32, 128)),
+                                             ((4096, 11008), (2, 256)), ((520, 264), (3, 5))])
+def test_dynamic_quant_linear_matches_oracle(dtype, name, features, tokens):
+    """BASELINE.json configs[0] (4096x4096, 16 tokens) and configs[1] (BERT-base, 32x128) among others."""
+    fin, fout = features
+    torch.manual_seed(0)
+    lin = nn.Linear(fin, fout).to(dtype)
+    x = torch.randn(*tokens, fin).to(dtype)
+    m = pq.DynamicQuantLinear.from_float(lin.cuda())
+    before = pq.launch_count()
+    y = m(x.cuda())
+    assert pq.launch_count() - before == 2          # act-quant + fused GEMM, nothing else
+    assert y.shape == (*tokens, fout) and y.dtype == dtype
+    wq, sw = O.quantize_weight(lin.weight.detach())
+    ref = O.qlinear(x, wq, sw, lin.bias.detach().float().numpy(), out_dtype=name)
+    assert torch.equal(_bits(y.cpu()), _bits(ref))
+    fl = lin.float()(x.float())
+    assert (y.cpu().float() - fl).abs().max() < 0.06 * fl.abs().max()
+
+
+def test_swap_linear_on_an_mlp_block():
+    torch.manual_seed(1)
+
+    class MLP(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.up = nn.Linear(256, 1024)
+            self.act = nn.GELU()
+            self.down = nn.Linear(1024, 256)
+            self.tiny = nn.Linear(256, 8)
+
+        def forward(self, x):
+            return self.tiny(self.down(self.act(self.up(x))))
+
+    net = MLP().to(torch.bfloat16).cuda()
+    x = torch.randn(64, 256, dtype=torch.bfloat16, device="cuda")
+    ref = net(x)
+    pq.swap_linear(net, min_features=64)
+    assert isinstance(net.up, pq.DynamicQuantLinear) and isinstance(net.down, pq.DynamicQuantLinear)
+    assert isinstance(net.tiny, nn.Linear)              # below min_features -> untouched
+    y = net(x)
+    assert (y.float() - ref.float()).abs().max() < 0.1 * ref.float().abs().max() + 0.05
+    sd = net.state_dict()
+    assert sd["up.qweight_storage"].dtype == torch.int8 and sd["up.weight_scale"].dtype == torch.float32
+
+
+def test_host_buffer_c_api_roundtrip():
+    """pq_linear_create / pq_linear_forward_host: the call bench.py's e2e number goes through."""
+    lib = pq.lib()
+    N, K, M = 512, 768, 100
+    g = torch.Generator().manual_seed(2)
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5).contiguous()
+    b = torch.randn(N, generator=g).contiguous()
+    x = torch.randn(M, K, generator=g).to(torch.bfloat16).contiguous().pin_memory()
+    y = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
+    h = ctypes.c_void_p()
+    assert lib.pq_linear_create(ctypes.byref(h), w.data_ptr(), 0, N, K, b.data_ptr(), 128, 2, 2, None) == 0
+    try:
+        assert lib.pq_linear_forward_host(h, x.data_ptr(), y.data_ptr(), M) == 0
+        wq, sw = O.quantize_weight(w)
+        ref = O.qlinear(x, wq, sw, b.numpy(), out_dtype="bf16")
+        assert torch.equal(_bits(y), _bits(ref))
+        assert lib.pq_linear_forward_host(h, x.data_ptr(), y.data_ptr(), 129) == 1   # > max_tokens
+    finally:
+        lib.pq_linear_destroy(h)
+
+
+def test_sharded_module_single_rank_equals_unsharded():
+    torch.manual_seed(3)
+    lin = nn.Linear(512, 1000).to(torch.bfloat16).cuda()
+    m = pq.DynamicQuantLinear.from_float(lin)
+    sh = pq.ShardedDynamicQuantLinear(m.qweight, m.weight_scale, m.bias)
+    x = torch.randn(77, 512, dtype=torch.bfloat16, device="cuda")
+    assert torch.equal(sh(x), m(x))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_module_nccl_bit_identical():
+    n = min(torch.cuda.device_count(), 8)
+    n = 1 << (n.bit_length() - 1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "_sharded_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "SHARDED_OK" in p.stdout

@@ -1,0 +1,118 @@
+"""CPU tests of the host-side logic: shard arithmetic, padded int8 allocation, module
+construction/state_dict, compat alias table, and the world_size-2 gloo run of the
+column-parallel path (oracle standing in for the kernel, as SURVEY.md §4 prescribes)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+import protoquant_b200 as pq
+from protoquant_b200 import compat, functional as F
+import protoquant_oracle as O
+
+
+def test_shard_bounds_cover_and_align():
+    for n in (8192, 28672, 11008, 4096, 1000, 7):
+        for world in (1, 2, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = pq.shard_bounds(n, world, r)
+                assert lo == prev and lo <= hi <= n
+                if hi < n:
+                    assert (hi - lo) % 8 == 0
+                prev = hi
+            assert prev == n
+
+
+def test_alloc_q_pads_row_stride_to_16_bytes():
+    for k in (1, 15, 16, 100, 4096, 11008):
+        t = F.alloc_q(3, k, "cpu")
+        assert t.shape == (3, k) and t.stride(0) % 16 == 0 and t.stride(1) == 1
+
+
+def test_module_construction_and_state_dict_roundtrip():
+    m = pq.DynamicQuantLinear(100, 24, bias=True)
+    assert m.qweight.shape == (24, 100) and m.qweight.stride(0) == 112
+    sd = m.state_dict()
+    assert set(sd) == {"qweight_storage", "weight_scale", "bias"}
+    m2 = pq.DynamicQuantLinear(100, 24, bias=True)
+    m.weight_scale.fill_(0.5)
+    m2.load_state_dict(m.state_dict())
+    assert torch.equal(m2.weight_scale, m.weight_scale)
+    assert "int8" in repr(m)
+
+
+def test_compat_alias_table():
+    assert compat.QLinear is pq.DynamicQuantLinear
+    assert compat.quantize_per_token is pq.quantize_act
+    for name in compat.__all__:
+        assert hasattr(compat, name)
+
+
+def test_qtensor_metadata():
+    qt = pq.QTensor(torch.zeros(6, 8, dtype=torch.int8), torch.ones(6), orig_dtype=torch.bfloat16, orig_shape=(2, 3, 8))
+    assert qt.shape == (2, 3, 8) and qt.axis == -1
+    assert "QTensor" in repr(qt)
+    with pytest.raises(NotImplementedError):
+        pq.quantize(torch.zeros(4, 4), axis=0)
+
+
+# ---- world_size 2 over gloo ------------------------------------------------------------
+def _oracle_local(x2, wq, s_w, bias, out_dtype):
+    name = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[out_dtype]
+    return O.qlinear(x2, wq.numpy(), s_w.numpy(), None if bias is None else bias.numpy(), out_dtype=name)
+
+
+def _worker(rank, world, port, N, K, M, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        w = (torch.rand(N, K) * 2 - 1) / K ** 0.5
+        b = torch.randn(N)
+        x = torch.randn(M, K).to(torch.bfloat16)
+        wq, sw = O.quantize_rowwise(w)
+        full = O.qlinear(x, wq, sw, b.numpy(), out_dtype="bf16")
+        lin = pq.ShardedDynamicQuantLinear(torch.from_numpy(wq), torch.from_numpy(sw), b, local_forward=_oracle_local)
+        y = lin(x)
+        lo, hi = pq.shard_bounds(N, world, rank)
+        ok = torch.equal(y, full) and (lin.lo, lin.hi) == (lo, hi) and y.shape == (M, N)
+        y3 = lin(x.reshape(2, M // 2, K))
+        ok = ok and torch.equal(y3.reshape(M, N), full)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("N", [64, 100])   # 100: last shard is ragged (56 + 44)
+def test_column_parallel_gloo_world2_bit_identical(N):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, 96, 6, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_maybe_shard_keeps_small_layers_replicated():
+    m = pq.DynamicQuantLinear(64, 32)
+    assert pq.maybe_shard(m) is m
