@@ -446,6 +446,8 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
     case 2: return launch_cfg<1, 128, 6, OutT>(a, lda, b, ldb, g, num_sms, st);
     case 3: return launch_cfg<1, 64, 8, OutT>(a, lda, b, ldb, g, num_sms, st);
     case 4: return launch_cfg<2, 128, 8, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 5: return launch_cfg<2, 256, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 6: return launch_cfg<2, 256, 3, OutT>(a, lda, b, ldb, g, num_sms, st);
     default: PQ_FAIL(PQ_ERR_ARG, "qgemm: unknown tile config %d", cfg);
   }
 }

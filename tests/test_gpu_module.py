@@ -35,6 +35,7 @@ def test_dynamic_quant_linear_matches_oracle(dtype, name, features, tokens):
     y = m(x.cuda())
     assert pq.launch_count() - before == 2          # act-quant + fused GEMM, nothing else
     assert y.shape == (*tokens, fout) and y.dtype == dtype
+    lin = lin.cpu()
     wq, sw = O.quantize_weight(lin.weight.detach())
     ref = O.qlinear(x, wq, sw, lin.bias.detach().float().numpy(), out_dtype=name)
     assert torch.equal(_bits(y.cpu()), _bits(ref))
