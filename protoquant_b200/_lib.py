@@ -64,9 +64,13 @@ def _declare(lib):
     lib.pq_linear_forward_host.argtypes = [vp, vp, vp, i64]
     lib.pq_linear_destroy.restype = None
     lib.pq_linear_destroy.argtypes = [vp]
-    if hasattr(lib, "pq_debug_set_gemm_config"):
-        lib.pq_debug_set_gemm_config.restype = None
-        lib.pq_debug_set_gemm_config.argtypes = [i32]
+    if hasattr(lib, "pq_debug_set_timeline"):
+        lib.pq_debug_set_timeline.restype = None
+        lib.pq_debug_set_timeline.argtypes = [vp]
+    for dbg in ("pq_debug_set_gemm_config", "pq_debug_set_streamk"):
+        if hasattr(lib, dbg):
+            getattr(lib, dbg).restype = None
+            getattr(lib, dbg).argtypes = [i32]
 
 
 def lib():

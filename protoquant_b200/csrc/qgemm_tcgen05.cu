@@ -50,6 +50,10 @@ struct GemmArgs {
   void* out;
   long long ldo;  // elements
   int vec_ok;     // rows of `out` are 16-byte aligned
+  // stream-K (exact: int32 partial sums are associative). Null workspace = data-parallel tiles.
+  int32_t* sk_ws;     // [workers][2][CG][BN*128] int32 partial sums
+  int* sk_flags;      // [workers*CG][2] ticket / done counters (self-cleaning, zero between launches)
+  unsigned long long* tl;   // debug timeline (32 x u64 per CTA) or null
 };
 
 // ---- descriptors -----------------------------------------------------------------
@@ -84,6 +88,7 @@ struct SmemLayout {
   static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;     // full[S], empty[S], tfull[2], tempty[2]
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+  static constexpr int OFF_MISC = OFF_TMEM_PTR + 8;           // stream-K ticket broadcast
   static constexpr int TOTAL = OFF_TMEM_PTR + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
@@ -131,6 +136,77 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   n_blk = within / gsize;
 }
 
+// Work scheduler shared by the three roles.  A "segment" is a K-range [kb0,kb1) of one tile.
+//  data-parallel: worker w owns whole tiles w, w+W, w+2W, ...
+//  stream-K:      the T*KB (tile, k-block) units are cut into W equal contiguous ranges.  A
+//                 worker first does the (at most two) PARTIAL tiles at the ends of its range and
+//                 only then its whole tiles, so every cross-worker fix-up happens early and is
+//                 hidden behind the main loops of the whole tiles that follow.
+// int32 accumulation is associative, so any split of K is bit-identical to the unsplit GEMM.
+struct Sched {
+  int KB, num_tiles, tile, stride;
+  bool sk;
+  long long U, u0, u1;
+  int worker, workers, phase, t_full, t_full_end;
+  __device__ __forceinline__ void init(const GemmArgs& g, int w, int W) {
+    KB = g.num_k_blocks;
+    num_tiles = g.num_m_blocks * g.num_n_blocks;
+    sk = g.sk_ws != nullptr;
+    worker = w; workers = W;
+    tile = w; stride = W;
+    U = 0; u0 = 0; u1 = 0; phase = 0; t_full = 0; t_full_end = 0;
+    if (sk) {
+      U = (long long)num_tiles * KB;
+      u0 = U * w / W;
+      u1 = U * (w + 1) / W;
+      t_full = (int)((u0 + KB - 1) / KB);
+      t_full_end = (int)(u1 / KB);
+    }
+  }
+  __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
+    if (!sk) {
+      if (tile >= num_tiles) return false;
+      t = tile; kb0 = 0; kb1 = KB; tile += stride;
+      return true;
+    }
+    if (u0 >= u1) return false;
+    if (phase == 0) {
+      phase = 1;
+      const long long tf = u0 / KB;
+      if (u0 != tf * KB) {                       // tail (or an inner piece) of the first tile
+        const long long te = (tf + 1) * KB;
+        t = (int)tf; kb0 = (int)(u0 - tf * KB); kb1 = (int)((u1 < te ? u1 : te) - tf * KB);
+        return true;
+      }
+    }
+    if (phase == 1) {
+      phase = 2;
+      const long long tl = u1 / KB;
+      if (u1 != tl * KB && tl * KB >= u0) {      // head of the last tile
+        t = (int)tl; kb0 = 0; kb1 = (int)(u1 - tl * KB);
+        return true;
+      }
+    }
+    if (t_full < t_full_end) {
+      t = t_full++; kb0 = 0; kb1 = KB;
+      return true;
+    }
+    return false;
+  }
+  // worker whose range contains unit u
+  __device__ __forceinline__ int worker_of_unit(long long u) const {
+    return (int)(((u + 1) * workers - 1) / U);
+  }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+#define PQ_TL(i) do { if (g.tl) g.tl[(size_t)blockIdx.x * 32 + (i)] = globaltimer_ns(); } while (0)
+
 template <int CG, int BN, int STAGES, typename OutT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -161,8 +237,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::OFF_TMEM_PTR);
   float* sw_smem = reinterpret_cast<float*>(smem_gen + L::OFF_SW);
   float* bias_smem = reinterpret_cast<float*>(smem_gen + L::OFF_BIAS);
+  volatile int* misc_smem = reinterpret_cast<volatile int*>(smem_gen + L::OFF_MISC);
 
   if (warp == 0 && lane == 0) {
+    PQ_TL(0);
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
   }
@@ -189,19 +267,21 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int num_clusters = gridDim.x / CG;
   const int cluster_id = blockIdx.x / CG;
-  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
-  const int num_kb = g.num_k_blocks;
+  Sched sched;
+  sched.init(g, cluster_id, num_clusters);
+  if (threadIdx.x == 0) PQ_TL(1);
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int tile, kb0, kb1;
+      while (sched.next(tile, kb0, kb1)) {
         int m_blk, n_blk;
         tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
         const int m_idx = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
         const int n_idx = n_blk * BN + (int)cta_rank * L::B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1);
           const uint32_t sa = smem_base + L::OFF_A + stage * L::A_STAGE;
           const uint32_t sb = smem_base + L::OFF_B + stage * L::B_STAGE;
@@ -217,8 +297,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive_remote(fb, 0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (g.tl && g.tl[(size_t)blockIdx.x * 32 + 2] == 0) PQ_TL(2);
         }
       }
+      PQ_TL(3);
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
@@ -226,27 +308,30 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       constexpr uint32_t idesc = make_idesc(UMMA_M, UMMA_N);
       uint32_t stage = 0, phase = 0;
       int iter = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      int tile, kb0, kb1;
+      for (; sched.next(tile, kb0, kb1); ++iter) {
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(bar_tempty + as * 8, aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
+          if (g.tl && g.tl[(size_t)blockIdx.x * 32 + 4] == 0) PQ_TL(4);
           const uint64_t adesc = make_smem_desc(smem_base + L::OFF_A + stage * L::A_STAGE);
           const uint64_t bdesc = make_smem_desc(smem_base + L::OFF_B + stage * L::B_STAGE);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr>>4) field
             mma_i8<CG>(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
+                       idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           tc_commit<CG>(bar_empty + stage * 8);
-          if (kb == num_kb - 1) tc_commit<CG>(bar_tfull + as * 8);
+          if (kb == kb1 - 1) tc_commit<CG>(bar_tfull + as * 8);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      PQ_TL(5);
       // Drain: the peer CTA's epilogue arrives on OUR tmem_empty barriers; do not let this
       // CTA exit (and its shared memory be reclaimed) before those arrivals have landed.
       if (CG == 2 && iter > 0) {
@@ -263,12 +348,78 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int ew = warp - EPI_WARP0;             // == warp % 4: TMEM lane quarter this warp may read
     const int et = ew * 32 + (int)lane;          // row inside the CTA's 128-row slab
     int iter = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+    int tile, kb0, kb1;
+    for (; sched.next(tile, kb0, kb1); ++iter) {
       int m_blk, n_blk;
       tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
       const int row = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M + et;
       const int col0 = n_blk * BN;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
+      constexpr long long SLOT = (long long)BN * BLOCK_M;   // int32 elements per CTA partial
+      // ---- stream-K: a split tile is completed by whichever participant finishes last ----
+      // Every participant takes a ticket once its own accumulator is complete.  All but the last
+      // dump their raw int32 partial into their own workspace slot (plain coalesced stores) and
+      // bump `done`; the last one folds the others' partials into its registers and runs the
+      // normal epilogue.  A worker has at most two partial segments -> two slots per worker.
+      int role = 0;   // 0 whole tile, 1 contributor, 2 combiner
+      int* ctr = nullptr;   // ctr[0] = tickets taken, ctr[1] = contributions finished
+      int fw = 0, lw = -1;
+      const bool split = (kb0 != 0 || kb1 != sched.KB);
+      if (split) {
+        mbar_wait(bar_tfull + as * 8, aphase);
+        if (et == 0 && iter < 5) PQ_TL(8 + iter * 4 + 0);
+        fw = sched.worker_of_unit((long long)tile * sched.KB);
+        lw = sched.worker_of_unit((long long)(tile + 1) * sched.KB - 1);
+        ctr = g.sk_flags + 2 * (fw * CG + (int)cta_rank);
+        if (et == 0) *misc_smem = atomicAdd(ctr, 1);
+        named_bar_sync(1, EPI_THREADS);
+        role = (*misc_smem == lw - fw) ? 2 : 1;
+        if (et == 0 && iter < 5) { PQ_TL(8 + iter * 4 + 1); if (g.tl) g.tl[(size_t)blockIdx.x * 32 + 28 + (iter & 3)] = (unsigned long long)role * 1000 + (lw - fw + 1); }
+      }
+      if (role == 1) {
+        tc_fence_after();
+        __syncwarp();
+        int32_t* slot = g.sk_ws + (((long long)sched.worker * 2 + (kb0 != 0 ? 0 : 1)) * CG + cta_rank) * SLOT;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + c * 32, r);
+          tmem_ld_wait();
+          if (row < g.M && col0 + c * 32 < g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcg(slot + (c * 32 + j) * BLOCK_M + et, (int)r[j]);
+          }
+        }
+        tc_fence_before();
+        if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
+        else mbar_arrive_remote(bar_tempty + as * 8, 0);
+        __threadfence();
+        named_bar_sync(1, EPI_THREADS);
+        if (et == 0) atomicAdd(ctr + 1, 1);
+        if (et == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
+        continue;
+      }
+      if (role == 2) {
+        if (et == 0) {
+          uint32_t polls = 0;
+          uint64_t t0 = 0;
+          while (ld_acquire_gpu(ctr + 1) != lw - fw) {
+            if ((++polls & 1023u) == 0) {
+              const uint64_t now = globaltimer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > PQ_MBAR_TIMEOUT_NS) {
+                printf("pq: stream-K wait timed out (block %d tile %d)\n", (int)blockIdx.x, tile);
+                __trap();
+              }
+            }
+          }
+          ctr[0] = 0;   // self-cleaning: the next launch finds the counters at zero
+          ctr[1] = 0;
+          if (iter < 5) PQ_TL(8 + iter * 4 + 2);
+        }
+        named_bar_sync(1, EPI_THREADS);
+      }
       float sx = 0.f;
       if constexpr (!RAW) {
         // stage this tile's column scales / bias (double-buffered by accumulator stage)
@@ -285,7 +436,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(bar_tfull + as * 8, aphase);
       tc_fence_after();
       __syncwarp();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -293,6 +443,17 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld_wait();
         const int col = col0 + c * 32;
         if (row < g.M && col < g.N) {
+          if (role == 2) {
+            // fold in the other participants' partial sums (slot 0 = their first-tile tail,
+            // slot 1 = their last-tile head)
+            for (int q = fw; q <= lw; ++q) {
+              if (q == sched.worker) continue;
+              const int which = (sched.U * q / sched.workers > (long long)tile * sched.KB) ? 0 : 1;
+              const int32_t* ps = g.sk_ws + (((long long)q * 2 + which) * CG + cta_rank) * SLOT + (c * 32) * BLOCK_M + et;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] += (uint32_t)__ldcg(ps + j * BLOCK_M);
+            }
+          }
           if constexpr (RAW) {
             int32_t* dst = reinterpret_cast<int32_t*>(g.out) + (long long)row * g.ldo + col;
             if (g.vec_ok && col + 32 <= g.N) {
@@ -339,6 +500,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
+      if (et == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
       // accumulator buffer fully read: hand it back to the MMA warp (leader CTA's barrier)
       tc_fence_before();
       if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
@@ -347,9 +509,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   __syncwarp();
+  if (threadIdx.x == 0) PQ_TL(6);
   tc_fence_before();
   if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) PQ_TL(7);
 }
 
 // ---- host side ---------------------------------------------------------------------
@@ -381,6 +545,66 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t kbytes, in
   return PQ_OK;
 }
 
+// ---- stream-K workspace pool ----------------------------------------------------------
+// One slot = partial-accumulator space for every worker CTA (num_sms x 2 x 128 x 256 int32) plus
+// two counters per CTA.  A slot is bound to the first stream that uses it, so kernels that can run
+// concurrently (different streams) never share partials.  Slots are allocated outside stream
+// capture only; one spare slot is kept ready so that a capturing stream (CUDA graphs) can be
+// bound without calling cudaMalloc.  If no slot can be had the launch silently uses the
+// data-parallel schedule (same results, int32 accumulation is exact either way).
+constexpr int SK_MAX_SLOTS = 8;
+struct SkSlot { int32_t* ws; int* flags; cudaStream_t stream; bool bound; };
+struct SkPool {
+  std::mutex mu;
+  SkSlot slots[SK_MAX_SLOTS];
+  int count = 0;
+};
+SkPool g_sk_pool[64];
+unsigned long long* g_timeline = nullptr;
+int g_sk_mode = 0;   // 0 never (default until the fix-up path is cheap enough), 1 whenever legal, -1 heuristic
+
+bool sk_alloc_slot(SkPool& pool, int num_sms) {
+  if (pool.count >= SK_MAX_SLOTS) return false;
+  const size_t ws_bytes = (size_t)num_sms * 2 * BLOCK_M * 256 * sizeof(int32_t);
+  void* ws = nullptr;
+  void* fl = nullptr;
+  if (cudaMalloc(&ws, ws_bytes) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  if (cudaMalloc(&fl, (size_t)num_sms * 2 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(fl, 0, (size_t)num_sms * 2 * sizeof(int)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(ws);
+    if (fl) cudaFree(fl);
+    return false;
+  }
+  SkSlot& sl = pool.slots[pool.count++];
+  sl.ws = (int32_t*)ws; sl.flags = (int*)fl; sl.stream = nullptr; sl.bound = false;
+  return true;
+}
+
+// returns the slot bound to `st` (binding / allocating if possible), or nullptr
+SkSlot* sk_get_slot(int dev, int num_sms, cudaStream_t st) {
+  SkPool& pool = g_sk_pool[dev];
+  std::lock_guard<std::mutex> lk(pool.mu);
+  for (int i = 0; i < pool.count; ++i)
+    if (pool.slots[i].bound && pool.slots[i].stream == st) return &pool.slots[i];
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
+  SkSlot* free_slot = nullptr;
+  for (int i = 0; i < pool.count; ++i)
+    if (!pool.slots[i].bound) { free_slot = &pool.slots[i]; break; }
+  if (!free_slot && !capturing && sk_alloc_slot(pool, num_sms)) free_slot = &pool.slots[pool.count - 1];
+  if (!free_slot) return nullptr;
+  free_slot->bound = true;
+  free_slot->stream = st;
+  if (!capturing) {   // keep one spare ready for a future capturing stream
+    bool spare = false;
+    for (int i = 0; i < pool.count; ++i) spare |= !pool.slots[i].bound;
+    if (!spare) sk_alloc_slot(pool, num_sms);
+  }
+  return free_slot;
+}
+
 template <int CG, int BN, int STAGES, typename OutT>
 int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g0,
                int num_sms, cudaStream_t st) {
@@ -406,7 +630,29 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
 
   const long long tiles = (long long)g.num_m_blocks * g.num_n_blocks;
   long long clusters = num_sms / CG;
-  if (tiles < clusters) clusters = tiles;
+  // Stream-K when whole tiles would leave SMs idle: fewer tiles than workers (small M: the
+  // weight stream is spread over all SMs) or a ragged last wave.
+  {
+    const long long W = num_sms / CG;
+    const long long units = tiles * g.num_k_blocks;
+    const long long waves = (tiles + W - 1) / W;
+    const double eff = (double)tiles / (double)(waves * W);
+    bool want = (g_sk_mode == 1) || (g_sk_mode < 0 && eff < 0.95 && waves <= 8);
+    long long w_sk = W;
+    if (units / 4 < w_sk) w_sk = units / 4;     // at least ~4 K blocks per worker
+    if (w_sk < 2 || tiles % w_sk == 0) want = false;
+    if (want && g_sk_mode != 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      SkSlot* sl = sk_get_slot(dev, num_sms, st);
+      if (sl) {
+        g.sk_ws = sl->ws;
+        g.sk_flags = sl->flags;
+        clusters = w_sk;
+      }
+    }
+  }
+  if (g.sk_ws == nullptr && tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG), 1, 1);
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
@@ -437,7 +683,7 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
     const long long t256 = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
     if (g.M > 128 && t256 * 2 >= num_sms) cfg = 1;
     else if (g.M > 128) cfg = 4;
-    else if ((long long)((g.N + 127) / 128) >= num_sms) cfg = 2;
+    else if (g.N >= 1024) cfg = 0;   // small M: wide 1-CTA tiles, K split across SMs by stream-K
     else cfg = 3;
   }
   switch (cfg) {
@@ -475,6 +721,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   g.out = out; g.ldo = ldo;
   const int esz = dtype_size(out_dtype);
   g.vec_ok = (((uintptr_t)out & 15) == 0) && ((ldo * esz) % 16 == 0);
+  g.tl = g_timeline;
   switch (out_dtype) {
     case PQ_BF16: return launch_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
     case PQ_F16: return launch_typed<__half>(a, lda, b, ldb, g, num_sms, stream);
@@ -489,3 +736,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
 // Test/bench hook (not part of the reference-facing API): force a tile configuration,
 // -1 restores the heuristic.
 extern "C" void pq_debug_set_gemm_config(int cfg) { pq::g_force_cfg = cfg; }
+// -1 = heuristic, 0 = never use stream-K, 1 = use stream-K whenever it is legal
+extern "C" void pq_debug_set_streamk(int mode) { pq::g_sk_mode = mode; }
+// device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
+extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline = dev_buf; }

@@ -23,6 +23,7 @@ CONFIGS = [-1, 0, 1, 2, 3, 4]   # -1 = heuristic; see launch_typed() in csrc/qge
 def _reset_cfg():
     yield
     pq.lib().pq_debug_set_gemm_config(-1)
+    pq.lib().pq_debug_set_streamk(-1)
 
 
 def rand_i8(shape, seed):
@@ -34,23 +35,27 @@ def cpu_int_mm(a, b):
     return torch.from_numpy(O.int_mm(a.numpy(), b.numpy()))
 
 
+@pytest.mark.parametrize("sk", [0, 1])   # 0 = data-parallel tiles only, 1 = stream-K whenever legal
 @pytest.mark.parametrize("cfg", CONFIGS)
 @pytest.mark.parametrize("shape", [
     (1, 8, 16), (1, 64, 16), (16, 4096, 4096), (17, 40, 144), (128, 256, 128), (129, 257, 130),
     (256, 256, 256), (300, 520, 1040), (384, 768, 768), (255, 1000, 3072), (512, 3072, 768),
 ])
-def test_int32_accumulators_bit_exact(cfg, shape):
+def test_int32_accumulators_bit_exact(cfg, shape, sk):
     M, N, K = shape
     pq.lib().pq_debug_set_gemm_config(cfg)
+    pq.lib().pq_debug_set_streamk(sk)
     a, b = rand_i8((M, K), 1), rand_i8((N, K), 2)
     got = pq.qgemm_i32(a.cuda(), b.cuda())
     assert torch.equal(got.cpu(), cpu_int_mm(a, b))
 
 
+@pytest.mark.parametrize("sk", [0, 1])
 @pytest.mark.parametrize("cfg", [0, 1, 4])
 @pytest.mark.parametrize("shape", [(2048, 4096, 4096), (2048, 11008, 4096), (2048, 4096, 11008),
                                    (4096, 3072, 768), (1024, 3584, 8192), (256, 8192, 28672)])
-def test_int32_full_size_shapes(cfg, shape):
+def test_int32_full_size_shapes(cfg, shape, sk):
+    pq.lib().pq_debug_set_streamk(sk)
     """BASELINE.json configs: Llama-7B (4096/11008, 2048 tokens), BERT (768/3072, 4096 tokens),
     Llama-70B column shard (28672/8 = 3584 out-channels, K=8192) and down-proj K=28672."""
     M, N, K = shape
@@ -89,20 +94,52 @@ def test_persistent_scheduler_many_tiles():
     """More tiles than CTAs in both dimensions, ragged on every edge -> exercises ring/phase wrap."""
     M, N, K = 1100, 5000, 400
     a, b = rand_i8((M, K), 9), rand_i8((N, K), 10)
-    for cfg in (0, 1, 2, 3, 4):
-        pq.lib().pq_debug_set_gemm_config(cfg)
-        assert torch.equal(pq.qgemm_i32(a.cuda(), b.cuda()).cpu(), cpu_int_mm(a, b)), cfg
+    for sk in (0, 1):
+        pq.lib().pq_debug_set_streamk(sk)
+        for cfg in (0, 1, 2, 3, 4):
+            pq.lib().pq_debug_set_gemm_config(cfg)
+            assert torch.equal(pq.qgemm_i32(a.cuda(), b.cuda()).cpu(), cpu_int_mm(a, b)), (cfg, sk)
+
+
+def test_streamk_repeated_launches_and_cuda_graph_replay():
+    """Self-cleaning flags: the same workspace slot must give identical results launch after launch,
+    on a second stream, and when the launches are replayed from a CUDA graph."""
+    pq.lib().pq_debug_set_streamk(1)
+    M, N, K = 2048, 4096, 4096
+    a, b = rand_i8((M, K), 21).cuda(), rand_i8((N, K), 22).cuda()
+    ref = cpu_int_mm(a.cpu(), b.cpu()).cuda()
+    for _ in range(5):
+        assert torch.equal(pq.qgemm_i32(a, b), ref)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            assert torch.equal(pq.qgemm_i32(a, b), ref)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s_x = torch.ones(M, device="cuda")
+    s_w = torch.ones(N, device="cuda")
+    y = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    with torch.cuda.graph(g):
+        for _ in range(3):
+            pq.qgemm(a, s_x, b, s_w, None, torch.float32, out=y)
+    for _ in range(4):
+        y.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref.float())
 
 
 def _bits(t):
     return t.view(torch.int32 if t.dtype == torch.float32 else torch.int16)
 
 
+@pytest.mark.parametrize("sk", [-1, 1])
 @pytest.mark.parametrize("cfg", [-1, 0, 1, 3])
 @pytest.mark.parametrize("out", [(torch.bfloat16, "bf16"), (torch.float16, "f16"), (torch.float32, "f32")])
 @pytest.mark.parametrize("shape,use_bias", [((256, 512, 512), True), ((100, 264, 272), False),
                                             ((16, 4096, 4096), True), ((700, 1000, 768), True)])
-def test_fused_epilogue_bit_exact_vs_oracle(cfg, out, shape, use_bias):
+def test_fused_epilogue_bit_exact_vs_oracle(cfg, out, shape, use_bias, sk):
+    pq.lib().pq_debug_set_streamk(sk)
     """y = cast(((float(acc)*s_x)*s_w)+bias): same fp32 op order as the oracle -> identical bits."""
     M, N, K = shape
     dt, name = out
