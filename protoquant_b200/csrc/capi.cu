@@ -10,6 +10,7 @@ namespace pq {
 
 static thread_local char tl_error[512] = "";
 std::atomic<uint64_t> g_launch_count{0};
+int g_pdl = 1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -55,6 +56,8 @@ extern "C" {
 int pq_version(void) { return PQ_VERSION; }
 const char* pq_last_error(void) { return tl_error; }
 uint64_t pq_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
+/* test/bench hook: 0 disables programmatic dependent launch */
+void pq_debug_set_pdl(int on) { g_pdl = on; }
 
 int pq_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
                  int8_t* xq, int64_t ldq, float* s_x, int transpose,

@@ -15,6 +15,7 @@ namespace pq {
 // ---- error plumbing (thread-local message, see pq_last_error) -------------------
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launch_count;
+extern int g_pdl;   // 1 = launch kernels with programmatic stream serialization (default)
 
 #define PQ_FAIL(code, ...)        \
   do {                            \

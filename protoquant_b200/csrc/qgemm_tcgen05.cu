@@ -7,16 +7,17 @@
 // Both operands are K-major (xq [M,K], Wq [N,K]), which is the native layout of
 // `tcgen05.mma.kind::i8` with K-major shared-memory descriptors.
 //
-// Structure (one persistent CTA -- or CTA pair -- per SM, 256 threads):
+// Structure (one persistent CTA -- or CTA pair -- per SM, 384 threads):
 //   warp 0   TMA producer: 128-byte-swizzled [rows x 128 B] boxes of A and B into a
 //            STAGES-deep shared-memory ring, completion on `full` mbarriers.
 //   warp 1   MMA issuer (one thread): 4 x tcgen05.mma (K=32 each) per ring slot into a
 //            TMEM accumulator; tcgen05.commit releases the slot (`empty`) and, after the
 //            last K block, publishes the accumulator (`tmem_full`).
 //   warp 2   TMEM allocate / free (2 accumulator buffers of BLOCK_N columns).
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, scale/bias/cast, 16-byte
-//            global stores; then hands the accumulator back (`tmem_empty`) so the MMA
-//            warp is already filling the other buffer meanwhile.
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns, scale/bias/cast, 16-byte
+//            global stores (warp w reads TMEM lane quarter w%4; warps 4-7 take the left
+//            half of the tile's columns, 8-11 the right half); then hands the accumulator
+//            back (`tmem_empty`) so the MMA warp is already filling the other buffer.
 // CG == 2 runs the same roles on a 2-CTA cluster with `cta_group::2`: the pair shares a
 // 256 x BLOCK_N tile, each CTA stages its own 128 rows of A and its half of B, the even
 // CTA issues the MMAs for both and multicasts the commits.
@@ -36,9 +37,9 @@ using namespace ptx;
 constexpr int BLOCK_M = 128;   // rows of A per CTA (= TMEM lanes)
 constexpr int BLOCK_K = 128;   // bytes (= int8 elements) per ring slot: one 128B swizzle atom
 constexpr int UMMA_K = 32;     // int8 elements per tcgen05.mma
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;   // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int GROUP_M = 16;    // tile rasterisation: m-blocks per L2 swizzle group
 
 struct GemmArgs {
@@ -217,7 +218,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   constexpr int UMMA_N = BN;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BLOCK_N must be a multiple of 32 in [32,256]");
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BLOCK_N must be a multiple of 64 in [64,256]");
   static_assert(UMMA_N % 16 == 0, "invalid UMMA N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -239,6 +240,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   float* bias_smem = reinterpret_cast<float*>(smem_gen + L::OFF_BIAS);
   volatile int* misc_smem = reinterpret_cast<volatile int*>(smem_gen + L::OFF_MISC);
 
+  griddep_launch_dependents();   // PDL: the next kernel may begin its own prologue
   if (warp == 0 && lane == 0) {
     PQ_TL(0);
     prefetch_tmap(&tmap_a);
@@ -264,6 +266,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // PDL: everything above overlapped the previous kernel's tail; from here on we touch global
+  // memory that kernel may have produced (xq, s_x) or may still be reading (y).
+  griddep_wait();
 
   const int num_clusters = gridDim.x / CG;
   const int cluster_id = blockIdx.x / CG;
@@ -345,8 +350,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= EPI_WARP0) {
     // ================= epilogue =================
-    const int ew = warp - EPI_WARP0;             // == warp % 4: TMEM lane quarter this warp may read
+    const int ew = (warp - EPI_WARP0) & 3;       // == warp % 4: TMEM lane quarter this warp may read
+    const int half = (warp - EPI_WARP0) >> 2;    // which half of the tile's columns this warp handles
     const int et = ew * 32 + (int)lane;          // row inside the CTA's 128-row slab
+    const int etid = (int)threadIdx.x - EPI_WARP0 * 32;   // 0..255
+    constexpr int CH = BN / 64;                  // 32-column chunks per warp
+    const int c_lo = half * CH, c_hi = c_lo + CH;
     int iter = 0;
     int tile, kb0, kb1;
     for (; sched.next(tile, kb0, kb1); ++iter) {
@@ -368,21 +377,21 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool split = (kb0 != 0 || kb1 != sched.KB);
       if (split) {
         mbar_wait(bar_tfull + as * 8, aphase);
-        if (et == 0 && iter < 5) PQ_TL(8 + iter * 4 + 0);
+        if (etid == 0 && iter < 5) PQ_TL(8 + iter * 4 + 0);
         fw = sched.worker_of_unit((long long)tile * sched.KB);
         lw = sched.worker_of_unit((long long)(tile + 1) * sched.KB - 1);
         ctr = g.sk_flags + 2 * (fw * CG + (int)cta_rank);
-        if (et == 0) *misc_smem = atomicAdd(ctr, 1);
+        if (etid == 0) *misc_smem = atomicAdd(ctr, 1);
         named_bar_sync(1, EPI_THREADS);
         role = (*misc_smem == lw - fw) ? 2 : 1;
-        if (et == 0 && iter < 5) { PQ_TL(8 + iter * 4 + 1); if (g.tl) g.tl[(size_t)blockIdx.x * 32 + 28 + (iter & 3)] = (unsigned long long)role * 1000 + (lw - fw + 1); }
+        if (etid == 0 && iter < 5) { PQ_TL(8 + iter * 4 + 1); if (g.tl) g.tl[(size_t)blockIdx.x * 32 + 28 + (iter & 3)] = (unsigned long long)role * 1000 + (lw - fw + 1); }
       }
       if (role == 1) {
         tc_fence_after();
         __syncwarp();
         int32_t* slot = g.sk_ws + (((long long)sched.worker * 2 + (kb0 != 0 ? 0 : 1)) * CG + cta_rank) * SLOT;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr0 + c * 32, r);
           tmem_ld_wait();
@@ -396,12 +405,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         else mbar_arrive_remote(bar_tempty + as * 8, 0);
         __threadfence();
         named_bar_sync(1, EPI_THREADS);
-        if (et == 0) atomicAdd(ctr + 1, 1);
-        if (et == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
+        if (etid == 0) atomicAdd(ctr + 1, 1);
+        if (etid == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
         continue;
       }
       if (role == 2) {
-        if (et == 0) {
+        if (etid == 0) {
           uint32_t polls = 0;
           uint64_t t0 = 0;
           while (ld_acquire_gpu(ctr + 1) != lw - fw) {
@@ -425,7 +434,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // stage this tile's column scales / bias (double-buffered by accumulator stage)
         float* sw = sw_smem + as * BN;
         float* bs = bias_smem + as * BN;
-        for (int i = et; i < BN; i += EPI_THREADS) {
+        for (int i = etid; i < BN; i += EPI_THREADS) {
           const int c = col0 + i;
           sw[i] = (c < g.N) ? __ldg(g.s_w + c) : 0.f;
           bs[i] = (g.bias != nullptr && c < g.N) ? __ldg(g.bias + c) : 0.f;
@@ -437,7 +446,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       __syncwarp();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr0 + c * 32, r);
         tmem_ld_wait();
@@ -500,7 +509,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
-      if (et == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
+      if (etid == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
       // accumulator buffer fully read: hand it back to the MMA warp (leader CTA's barrier)
       tc_fence_before();
       if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
@@ -658,13 +667,15 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = L::DYN_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CG;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;

@@ -21,10 +21,26 @@
 // low mantissa byte is the two's complement int8 (|q1| <= 127.01 always, so the
 // [-128,127] clamp of the reference formula can never fire for finite input).
 #include "common.cuh"
+#include "ptx.cuh"
 #include <type_traits>
 
 namespace pq {
 namespace {
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
 
@@ -165,6 +181,8 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
   const int64_t row = (int64_t)blockIdx.x * ROWS + row_in_cta;
   const bool row_ok = row < M;
 
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();   // x may be produced, and xq still be read, by the previous kernel
   const T* xr = x + (row_ok ? row : 0) * ldx;
   uint4 v[VPT];
 #pragma unroll
@@ -237,6 +255,8 @@ rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int6
                              int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
                              int transpose, int scale_mode, float eps) {
   __shared__ float red[8];
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   const int64_t row = blockIdx.x;
   const T* xr = x + row * ldx;
   float amax = 0.f;
@@ -271,6 +291,8 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
                                 float* __restrict__ s_out, int scale_mode, float eps) {
   __shared__ RowQ rowq[32];
   __shared__ int8_t tile[128][33];
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * 32;
   for (int r = warp; r < 32; r += 8) {
@@ -333,10 +355,9 @@ int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int6
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
   const int64_t grid = (M + ROWS - 1) / ROWS;
-  rowwise_quant_vec_kernel<T, TPR, VPT><<<(unsigned)grid, THREADS, 0, st>>>(
-      (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps);
+  PQ_CUDA(launch_pdl(rowwise_quant_vec_kernel<T, TPR, VPT>, (unsigned)grid, THREADS, st,
+                     (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  PQ_CUDA(cudaGetLastError());
   return PQ_OK;
 }
 
@@ -348,10 +369,9 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
   if (transpose) {
     const int64_t grid = (M + 31) / 32;
-    rowwise_quant_transposed_kernel<T><<<(unsigned)grid, 256, 0, st>>>(
-        (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps);
+    PQ_CUDA(launch_pdl(rowwise_quant_transposed_kernel<T>, (unsigned)grid, 256u, st,
+                       (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    PQ_CUDA(cudaGetLastError());
     return PQ_OK;
   }
   const bool vec_ok = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) &&
@@ -359,10 +379,9 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
                       (((uintptr_t)xq % EPV) == 0) && (ldq % EPV == 0) &&
                       (K / EPV <= 8192);
   if (!vec_ok) {
-    rowwise_quant_generic_kernel<T><<<(unsigned)M, 256, 0, st>>>(
-        (const T*)x, M, K, ldx, xq, ldq, s, 0, spec.scale_mode, spec.eps);
+    PQ_CUDA(launch_pdl(rowwise_quant_generic_kernel<T>, (unsigned)M, 256u, st,
+                       (const T*)x, M, K, ldx, xq, ldq, s, 0, spec.scale_mode, spec.eps));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    PQ_CUDA(cudaGetLastError());
     return PQ_OK;
   }
   const int nvec = (int)(K / EPV);

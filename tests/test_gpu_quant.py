@@ -120,7 +120,7 @@ def test_act_quant_large_properties():
     assert torch.equal(s, torch.div(amax, torch.full_like(amax, 127.0)))   # tensor/tensor: IEEE div (x/scalar is x*(1/scalar) on CUDA)
     assert bool((q.abs().amax(dim=1) == 127).all()) and int(q.min()) >= -127
     err = (q.float() * s[:, None] - xf).abs()
-    assert bool((err <= s[:, None] * 0.5000001).all())
+    assert bool((err <= s[:, None] * 0.5001).all())      # 0.5 ulp of the int grid + fp32 rounding of x/s and q*s
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
