@@ -431,10 +431,11 @@ def sharded_leg(pq, torch, dist, dev, rank, world):
     full = pq.DynamicQuantLinear(K, N, bias=False, device=dev)
     full.qweight_storage[:, :K].copy_(wq_full)
     full.weight_scale.copy_(sw_full)
-    sh = pq.ShardedDynamicQuantLinear(wq_full, sw_full, None) if world > 1 else None
+    sh = pq.ShardedDynamicQuantLinear(wq_full, sw_full, None, fused=False) if world > 1 else None
+    shf = pq.ShardedDynamicQuantLinear(wq_full, sw_full, None, fused=None) if world > 1 else None
     for M in (16, 2048):
         x = torch.randn(M, K, device=dev, generator=g).to(torch.bfloat16)
-        for label, mod in (("replicated", full), ("sharded_allgather", sh)):
+        for label, mod in (("replicated", full), ("sharded_nccl_allgather", sh), ("sharded_fused_epilogue", shf)):
             if mod is None:
                 continue
             for _ in range(3):
@@ -455,11 +456,16 @@ def sharded_leg(pq, torch, dist, dev, rank, world):
                 ms = t.item()
             res[f"M{M}_{label}"] = {"ms": ms, "tops": 2 * M * N * K / (ms * 1e-3) / 1e12, "tokens_per_s": M / (ms * 1e-3)}
         if sh is not None:
-            res[f"M{M}_bit_identical"] = bool(torch.equal(sh(x), full(x)))
+            res[f"M{M}_bit_identical"] = bool(torch.equal(sh(x), full(x)) and torch.equal(shf(x), full(x)))
+    if shf is not None:
+        res["fused_path_active"] = bool(shf.fused)
     return res
 
 
 def main():
+    # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -88,6 +88,17 @@ int pq_qgemm(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
              void* y, int y_dtype, int64_t ldy,
              int64_t M, int64_t N, int64_t K, void* stream);
 
+/* SURVEY §8e — fused GEMM + all-gather store.  Same computation as pq_qgemm, but the [M,N]
+ * result is written to each of ys[0..n_ys) (1 <= n_ys <= 8).  For a column-parallel layer,
+ * rank r passes, for every peer p, the peer-mapped address of p's full output buffer offset to
+ * r's first column (NVLink peer stores issued from the GEMM epilogue), or a single NVSwitch
+ * multicast address; ldy is the row stride of the full buffer.  The caller provides the
+ * cross-rank barrier that follows. */
+int pq_qgemm_multi(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
+                   const float* s_x, const float* s_w, const float* bias,
+                   void* const* ys, int n_ys, int y_dtype, int64_t ldy,
+                   int64_t M, int64_t N, int64_t K, void* stream);
+
 /* Parity hook for row a3: raw int32 accumulators acc[M,N], row stride ldc (elements). */
 int pq_qgemm_i32(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
                  int32_t* acc, int64_t ldc,

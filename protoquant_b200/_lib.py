@@ -19,7 +19,7 @@ PQ_DIV, PQ_RCP_MUL, PQ_INV_SCALE = 0, 1, 2
 # every symbol include/protoquant_b200.h declares (tests/test_abi.py checks the .so exports them)
 EXPORTS = (
     "pq_version", "pq_last_error", "pq_launch_count", "pq_act_quant", "pq_weight_quant",
-    "pq_qgemm", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
+    "pq_qgemm", "pq_qgemm_multi", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
     "pq_linear_create", "pq_linear_forward_host", "pq_linear_destroy",
 )
 
@@ -52,6 +52,8 @@ def _declare(lib):
     lib.pq_weight_quant.argtypes = [vp, i32, i64, i64, i64, vp, i64, vp, specp, vp]
     lib.pq_qgemm.restype = i32
     lib.pq_qgemm.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp]
+    lib.pq_qgemm_multi.restype = i32
+    lib.pq_qgemm_multi.argtypes = [vp, i64, vp, i64, vp, vp, vp, c.POINTER(vp), i32, i32, i64, i64, i64, i64, vp]
     lib.pq_qgemm_i32.restype = i32
     lib.pq_qgemm_i32.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
     lib.pq_dequant.restype = i32

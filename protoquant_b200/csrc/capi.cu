@@ -83,12 +83,23 @@ int pq_qgemm(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
              int64_t M, int64_t N, int64_t K, void* stream) {
   if (y_dtype != PQ_BF16 && y_dtype != PQ_F16 && y_dtype != PQ_F32)
     PQ_FAIL(PQ_ERR_ARG, "pq_qgemm: y_dtype must be PQ_BF16, PQ_F16 or PQ_F32");
-  return launch_qgemm(xq, lda, Wq, ldb, s_x, s_w, bias, y, y_dtype, ldy, M, N, K, (cudaStream_t)stream);
+  void* outs[1] = {y};
+  return launch_qgemm(xq, lda, Wq, ldb, s_x, s_w, bias, outs, 1, y_dtype, ldy, M, N, K, (cudaStream_t)stream);
+}
+
+int pq_qgemm_multi(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
+                   const float* s_x, const float* s_w, const float* bias,
+                   void* const* ys, int n_ys, int y_dtype, int64_t ldy,
+                   int64_t M, int64_t N, int64_t K, void* stream) {
+  if (y_dtype != PQ_BF16 && y_dtype != PQ_F16 && y_dtype != PQ_F32)
+    PQ_FAIL(PQ_ERR_ARG, "pq_qgemm_multi: y_dtype must be PQ_BF16, PQ_F16 or PQ_F32");
+  return launch_qgemm(xq, lda, Wq, ldb, s_x, s_w, bias, ys, n_ys, y_dtype, ldy, M, N, K, (cudaStream_t)stream);
 }
 
 int pq_qgemm_i32(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
                  int32_t* acc, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream) {
-  return launch_qgemm(xq, lda, Wq, ldb, nullptr, nullptr, nullptr, acc, PQ_I32, ldc, M, N, K,
+  void* outs[1] = {acc};
+  return launch_qgemm(xq, lda, Wq, ldb, nullptr, nullptr, nullptr, outs, 1, PQ_I32, ldc, M, N, K,
                       (cudaStream_t)stream);
 }
 

@@ -48,7 +48,8 @@ struct GemmArgs {
   const float* s_x;
   const float* s_w;
   const float* bias;
-  void* out;
+  void* out[8];   // the [M,N] result is stored into each of out[0..n_out): the local buffer, peer
+  int n_out;      // buffers mapped over NVLink, or one NVSwitch multicast address (fused all-gather)
   long long ldo;  // elements
   int vec_ok;     // rows of `out` are 16-byte aligned
   // stream-K (exact: int32 partial sums are associative). Null workspace = data-parallel tiles.
@@ -464,15 +465,17 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
           if constexpr (RAW) {
-            int32_t* dst = reinterpret_cast<int32_t*>(g.out) + (long long)row * g.ldo + col;
-            if (g.vec_ok && col + 32 <= g.N) {
+            for (int d = 0; d < g.n_out; ++d) {
+              int32_t* dst = reinterpret_cast<int32_t*>(g.out[d]) + (long long)row * g.ldo + col;
+              if (g.vec_ok && col + 32 <= g.N) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                reinterpret_cast<uint4*>(dst)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-            } else {
+                for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<uint4*>(dst)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col + j < g.N) dst[j] = (int32_t)r[j];
+                for (int j = 0; j < 32; ++j)
+                  if (col + j < g.N) dst[j] = (int32_t)r[j];
+              }
             }
           } else {
             using OT = typename std::conditional<RAW, float, OutT>::type;
@@ -494,17 +497,22 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 f[4 * j4 + j] = v;
               }
             }
-            OT* dst = reinterpret_cast<OT*>(g.out) + (long long)row * g.ldo + col;
             if (g.vec_ok && col + 32 <= g.N) {
               uint32_t o[OutPack<OT>::WORDS];
               OutPack<OT>::pack(f, o);
+              for (int d = 0; d < g.n_out; ++d) {
+                OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)row * g.ldo + col;
 #pragma unroll
-              for (int i = 0; i < OutPack<OT>::WORDS / 4; ++i)
-                reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                for (int i = 0; i < OutPack<OT>::WORDS / 4; ++i)
+                  reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+              }
             } else {
+              for (int d = 0; d < g.n_out; ++d) {
+                OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)row * g.ldo + col;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col + j < g.N) dst[j] = OutPack<OT>::one(f[j]);
+                for (int j = 0; j < 32; ++j)
+                  if (col + j < g.N) dst[j] = OutPack<OT>::one(f[j]);
+              }
             }
           }
         }
@@ -713,12 +721,14 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
 
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,
-                 void* out, int out_dtype, int64_t ldo,
+                 void* const* outs, int n_out, int out_dtype, int64_t ldo,
                  int64_t M, int64_t N, int64_t K, cudaStream_t stream) {
   if (M < 0 || N < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "qgemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   if (M == 0 || N == 0) return PQ_OK;
   if (M > 0x7fffff00LL || N > 0x7fffff00LL || K > 0x7fffff00LL) PQ_FAIL(PQ_ERR_ARG, "qgemm: dimension too large");
-  if (!a || !b || !out) PQ_FAIL(PQ_ERR_ARG, "qgemm: null pointer");
+  if (!a || !b || !outs || n_out < 1 || n_out > 8) PQ_FAIL(PQ_ERR_ARG, "qgemm: null pointer or bad destination count");
+  for (int d = 0; d < n_out; ++d)
+    if (!outs[d]) PQ_FAIL(PQ_ERR_ARG, "qgemm: null destination %d", d);
   if (out_dtype != PQ_I32 && (!s_x || !s_w)) PQ_FAIL(PQ_ERR_ARG, "qgemm: null scale pointer");
   if (lda < K || ldb < K || ldo < N) PQ_FAIL(PQ_ERR_ARG, "qgemm: leading dimension too small");
   if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || (lda & 15) || (ldb & 15))
@@ -729,9 +739,14 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   GemmArgs g = {};
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.s_x = s_x; g.s_w = s_w; g.bias = bias;
-  g.out = out; g.ldo = ldo;
+  g.ldo = ldo;
+  g.n_out = n_out;
   const int esz = dtype_size(out_dtype);
-  g.vec_ok = (((uintptr_t)out & 15) == 0) && ((ldo * esz) % 16 == 0);
+  g.vec_ok = ((ldo * esz) % 16 == 0);
+  for (int d = 0; d < n_out; ++d) {
+    g.out[d] = outs[d];
+    if ((uintptr_t)outs[d] & 15) g.vec_ok = 0;
+  }
   g.tl = g_timeline;
   switch (out_dtype) {
     case PQ_BF16: return launch_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);

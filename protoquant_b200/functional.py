@@ -157,6 +157,28 @@ def qgemm(xq: torch.Tensor, s_x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tens
     return y
 
 
+def qgemm_multi(xq: torch.Tensor, s_x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tensor,
+                bias: Optional[torch.Tensor], dest_ptrs, ldy: int, out_dtype: torch.dtype) -> None:
+    """Fused GEMM + all-gather store: the [M,N] result is written to every raw device address in
+    `dest_ptrs` (row stride `ldy` elements).  The addresses are peer-mapped (NVLink) or NVSwitch
+    multicast pointers into the ranks' full output buffers, already offset to this rank's first
+    column; the caller issues the cross-rank barrier afterwards."""
+    xq = _gemm_operand(xq, "xq")
+    wq = _gemm_operand(wq, "wq")
+    M, K = xq.shape
+    N = wq.shape[0]
+    if not (1 <= len(dest_ptrs) <= 8):
+        raise ValueError("1..8 destinations")
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        bias = bias.to(torch.float32).contiguous()
+    arr = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
+    if M and N:
+        rc = _lib.lib().pq_qgemm_multi(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), s_x.data_ptr(),
+                                       s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       arr, len(dest_ptrs), _DT[out_dtype], ldy, M, N, K, _stream())
+        _lib.check(rc, "pq_qgemm_multi")
+
+
 def qlinear(x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             out_dtype: Optional[torch.dtype] = None, spec: Optional[QuantSpec] = None) -> torch.Tensor:
     """Dynamic-quant linear forward: x[...,K] -> y[...,N] with cached (wq, s_w)."""

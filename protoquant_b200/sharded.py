@@ -5,11 +5,23 @@ is replicated; every rank quantises it (cheap, HBM-bound), runs the int8 GEMM on
 slice and the output slices are all-gathered along N over NCCL/NVLink.  Column sharding does
 not change any accumulation order, so the gathered result is bit-identical to the 1-GPU one.
 
-The gather is the path's only exchange step.  `min_out_features` implements the north
-star's "used only for layers big enough to benefit": smaller layers stay replicated.
+The gather is the path's only exchange step.  Two implementations:
+
+* fused (default on CUDA when torch's symmetric memory can be set up): every rank owns a
+  symmetric [tokens, N] output buffer; the GEMM epilogue stores each finished tile straight
+  into ALL ranks' buffers -- one store to the NVSwitch multicast address when the fabric
+  supports it, else one NVLink peer store per rank -- so the transfer overlaps the MMAs tile
+  by tile and no separate collective or layout-fixing copy runs.  One symmetric-memory barrier
+  follows the kernel.  Output buffers are double-buffered: the tensor returned by forward() is
+  valid until the next-but-one forward() of the same module.
+* NCCL all-gather of the [tokens, N/G] slices (baseline; also the gloo path used by CPU tests).
+
+`min_out_features` implements the north star's "used only for layers big enough to benefit":
+smaller layers stay replicated.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -32,7 +44,7 @@ class ShardedDynamicQuantLinear(nn.Module):
     def __init__(self, qweight_full: torch.Tensor, weight_scale_full: torch.Tensor,
                  bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,
                  spec: Optional[F.QuantSpec] = None,
-                 local_forward: Optional[Callable] = None):
+                 local_forward: Optional[Callable] = None, fused: Optional[bool] = None):
         """qweight_full [N,K] int8, weight_scale_full [N] fp32, bias_full [N] fp32|None: the
         UNSHARDED quantised weight (every rank passes the same tensors; each keeps its slice).
         `local_forward(x2d, wq, s_w, bias, out_dtype)` defaults to the CUDA path; tests on a
@@ -45,6 +57,10 @@ class ShardedDynamicQuantLinear(nn.Module):
         self.out_dtype = out_dtype
         self.spec = spec
         self._local_forward = local_forward
+        # fused epilogue all-gather needs CUDA + symmetric memory; None = try it, fall back to NCCL
+        self.fused = fused
+        self._symm = None      # (capacity_rows, dtype) -> [(tensor, handle), (tensor, handle)]
+        self._flip = 0
         per = shard_bounds(self.out_features, self.world, 0)[1]
         self.per = per
         lo, hi = shard_bounds(self.out_features, self.world, self.rank)
@@ -74,10 +90,53 @@ class ShardedDynamicQuantLinear(nn.Module):
             return self._local_forward(x2, self.qweight, self.weight_scale, self.bias, out_dtype)
         return F.qlinear(x2, self.qweight, self.weight_scale, self.bias, out_dtype, self.spec)
 
+    # ---- fused path -------------------------------------------------------------------
+    def _symm_buffers(self, rows: int, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (dtype,)
+        if self._symm is not None and self._symm[0] == key and self._symm[1] >= rows:
+            return self._symm[2]
+        cap = max(rows, 16)
+        group = self.group if self.group is not None else dist.group.WORLD
+        bufs = []
+        for _ in range(2):
+            t = symm_mem.empty((cap, self.world * self.per), dtype=dtype, device=device)
+            h = symm_mem.rendezvous(t, group)
+            bufs.append((t, h))
+        self._symm = (key, cap, bufs)
+        return bufs
+
+    def _forward_fused(self, x2: torch.Tensor, out_dtype) -> torch.Tensor:
+        M = x2.shape[0]
+        bufs = self._symm_buffers(M, out_dtype, x2.device)
+        t, h = bufs[self._flip]
+        self._flip ^= 1
+        esz = t.element_size()
+        ld = self.world * self.per
+        off = self.rank * self.per * esz
+        mc = int(getattr(h, "multicast_ptr", 0) or 0) if getattr(h, "has_multicast_support", False) else 0
+        if mc and not os.environ.get("PQ_NO_MULTICAST"):
+            dests = [mc + off]
+        else:
+            dests = [int(p) + off for p in h.buffer_ptrs]
+        xq, s_x = F.quantize_act(x2, spec=self.spec)
+        F.qgemm_multi(xq, s_x, self.qweight, self.weight_scale, self.bias, dests, ld, out_dtype)
+        h.barrier()
+        return t[:M, : self.out_features]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         out_dtype = self.out_dtype or x.dtype
+        if self.world > 1 and self._local_forward is None and x2.is_cuda and self.fused is not False:
+            try:
+                y = self._forward_fused(x2, out_dtype)
+                self.fused = True
+                return y.reshape(*lead, self.out_features)
+            except Exception:
+                if self.fused is True:
+                    raise
+                self.fused = False       # symmetric memory unavailable: NCCL all-gather from now on
         y_local = self.local(x2, out_dtype).contiguous()          # [M, per]
         if self.world == 1:
             return y_local[:, : self.out_features].reshape(*lead, self.out_features)

@@ -23,9 +23,16 @@ def main():
         m = pq.DynamicQuantLinear.from_float(lin)
         x = torch.randn(M, K, dtype=torch.bfloat16, device="cuda")
         full = m(x)
-        sh = pq.ShardedDynamicQuantLinear(m.qweight, m.weight_scale, m.bias)
-        y = sh(x)
-        ok = ok and torch.equal(y, full)
+        for fused in (False, True):
+            sh = pq.ShardedDynamicQuantLinear(m.qweight, m.weight_scale, m.bias, fused=fused)
+            for _ in range(3):                      # repeated forwards exercise the double buffering
+                y = sh(x)
+                same = torch.equal(y, full)
+                ok = ok and same
+                if not same and rank == 0:
+                    print(f"MISMATCH N={N} K={K} M={M} fused={fused}")
+            if rank == 0:
+                print(f"N={N} K={K} M={M} fused={fused} -> {sh.fused}")
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
