@@ -77,7 +77,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
          ((uint32_t)(umma_m >> 4) << 24);
 }
 
-template <int CG, int BN, int STAGES>
+template <int CG, int BN, int STAGES, bool STAGED = false>
 struct SmemLayout {
   static constexpr int A_STAGE = BLOCK_M * BLOCK_K;
   static constexpr int B_ROWS = BN / CG;
@@ -85,7 +85,9 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
-  static constexpr int OFF_SW = OFF_B + STAGES * B_STAGE;   // [2][BN] fp32
+  static constexpr int STAGE_OUT = STAGED ? 2 * 32768 : 0;  // per column-half [128 rows][256 B] output staging
+  static constexpr int OFF_STAGE_OUT = OFF_B + STAGES * B_STAGE;
+  static constexpr int OFF_SW = OFF_STAGE_OUT + STAGE_OUT;  // [2][BN] fp32
   static constexpr int OFF_BIAS = OFF_SW + 2 * BN * 4;      // [2][BN] fp32
   static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;     // full[S], empty[S], tfull[2], tempty[2]
   static constexpr int NUM_BARS = 2 * STAGES + 4;
@@ -209,12 +211,17 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 
 #define PQ_TL(i) do { if (g.tl) g.tl[(size_t)blockIdx.x * 32 + (i)] = globaltimer_ns(); } while (0)
 
-template <int CG, int BN, int STAGES, typename OutT>
+// STAGED = true: the epilogue goes through shared memory so that every global store
+// instruction writes whole 256-byte row segments (needed for NVLink peer / multicast
+// destinations, where 16-byte scattered writes waste most of the link).
+template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
              const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
-  using L = SmemLayout<CG, BN, STAGES>;
+  using L = SmemLayout<CG, BN, STAGES, STAGED>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
+  static_assert(!(STAGED && RAW), "staged epilogue is for typed outputs only");
+  static_assert(!STAGED || BN == 256, "staged epilogue assumes 128-column halves");
   constexpr int UMMA_M = BLOCK_M * CG;
   constexpr int UMMA_N = BN;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -446,6 +453,88 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(bar_tfull + as * 8, aphase);
       tc_fence_after();
       __syncwarp();
+      if constexpr (STAGED) {
+        using OT = typename std::conditional<RAW, float, OutT>::type;
+        constexpr int ROWB = 256;                                  // staged bytes per row
+        constexpr int ESZ = (int)sizeof(OT);
+        constexpr int COLS_PASS = ROWB / ESZ;                      // 128 (16-bit) or 64 (fp32)
+        constexpr int CH_PASS = COLS_PASS / 32;
+        constexpr int PASSES = (BN / 2) / COLS_PASS;
+        constexpr int UPC = OutPack<OT>::WORDS / 4;                // 16-byte units per 32-column chunk
+        constexpr int EPU = 16 / ESZ;                              // elements per 16-byte unit
+        uint8_t* stg = smem_gen + L::OFF_STAGE_OUT + half * 32768;
+        const int gt = etid & 127;                                 // thread index inside this column half
+        const int m0 = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+#pragma unroll 1
+        for (int pass = 0; pass < PASSES; ++pass) {
+#pragma unroll 1
+          for (int cc = 0; cc < CH_PASS; ++cc) {
+            const int c = c_lo + pass * CH_PASS + cc;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr0 + c * 32, r);
+            tmem_ld_wait();
+            const float* sw = sw_smem + as * BN + c * 32;
+            const float* bs = bias_smem + as * BN + c * 32;
+            float f[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sw + 4 * j4);
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j4);
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+              const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v = __int2float_rn((int)r[4 * j4 + j]);
+                v = __fmul_rn(v, sx);
+                v = __fmul_rn(v, wv[j]);
+                v = __fadd_rn(v, bv[j]);
+                f[4 * j4 + j] = v;
+              }
+            }
+            uint32_t o[OutPack<OT>::WORDS];
+            OutPack<OT>::pack(f, o);
+#pragma unroll
+            for (int i = 0; i < UPC; ++i) {
+              const int u = cc * UPC + i;
+              *reinterpret_cast<uint4*>(stg + et * ROWB + ((u ^ (et & 7)) << 4)) =
+                  make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+          }
+          if (pass == PASSES - 1) {
+            // accumulator fully read: give the TMEM buffer back before the (slow) copy-out
+            tc_fence_before();
+            if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
+            else mbar_arrive_remote(bar_tempty + as * 8, 0);
+          }
+          if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
+          // copy-out: a warp instruction moves two whole 256-byte row segments per destination
+          const int colp = col0 + half * (BN / 2) + pass * COLS_PASS;
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int idx = i * 128 + gt;
+            const int rr = idx >> 4, u = idx & 15;
+            const int grow = m0 + rr;
+            const int gcol = colp + u * EPU;
+            if (grow < g.M && gcol < g.N) {
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * ROWB + ((u ^ (rr & 7)) << 4));
+              if (g.vec_ok && gcol + EPU <= g.N) {
+                for (int d = 0; d < g.n_out; ++d)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol) = v;
+              } else {
+                const OT* ev = reinterpret_cast<const OT*>(&v);
+                for (int d = 0; d < g.n_out; ++d) {
+                  OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol;
+#pragma unroll
+                  for (int e = 0; e < EPU; ++e)
+                    if (gcol + e < g.N) dst[e] = ev[e];
+                }
+              }
+            }
+          }
+          if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t r[32];
@@ -622,10 +711,10 @@ SkSlot* sk_get_slot(int dev, int num_sms, cudaStream_t st) {
   return free_slot;
 }
 
-template <int CG, int BN, int STAGES, typename OutT>
+template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false>
 int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g0,
                int num_sms, cudaStream_t st) {
-  using L = SmemLayout<CG, BN, STAGES>;
+  using L = SmemLayout<CG, BN, STAGES, STAGED>;
   GemmArgs g = g0;
   g.num_m_blocks = (g.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   g.num_n_blocks = (g.N + BN - 1) / BN;
@@ -636,7 +725,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   rc = make_tmap(&tb, b, g.N, g.K, ldb, L::B_ROWS);
   if (rc) return rc;
 
-  auto kern = qgemm_kernel<CG, BN, STAGES, OutT>;
+  auto kern = qgemm_kernel<CG, BN, STAGES, OutT, STAGED>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -654,7 +743,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
     const long long units = tiles * g.num_k_blocks;
     const long long waves = (tiles + W - 1) / W;
     const double eff = (double)tiles / (double)(waves * W);
-    bool want = (g_sk_mode == 1) || (g_sk_mode < 0 && eff < 0.95 && waves <= 8);
+    bool want = !STAGED && ((g_sk_mode == 1) || (g_sk_mode < 0 && eff < 0.95 && waves <= 8));
     long long w_sk = W;
     if (units / 4 < w_sk) w_sk = units / 4;     // at least ~4 K blocks per worker
     if (w_sk < 2 || tiles % w_sk == 0) want = false;
@@ -690,6 +779,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
 }
 
 int g_force_cfg = -1;  // test hook: see pq_debug_set_gemm_config
+int g_force_staged = 0;  // test hook: staged epilogue even for a single destination
 
 template <typename OutT>
 int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g,
@@ -697,6 +787,13 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
   // Tile configuration heuristic.
   //   cfg 0: 1-CTA 128x256   cfg 1: 2-CTA 256x256   cfg 2: 1-CTA 128x128   cfg 3: 1-CTA 128x64
   //   cfg 4: 2-CTA 256x128
+  if constexpr (!std::is_same<OutT, int32_t>::value) {
+    if (g.n_out > 1 || g_force_staged) {
+      // fused all-gather: coalesced (shared-memory staged) stores to every destination
+      if (g.M > 128) return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+      return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+    }
+  }
   int cfg = g_force_cfg;
   if (cfg < 0) {
     const long long t256 = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
@@ -764,5 +861,6 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
 extern "C" void pq_debug_set_gemm_config(int cfg) { pq::g_force_cfg = cfg; }
 // -1 = heuristic, 0 = never use stream-K, 1 = use stream-K whenever it is legal
 extern "C" void pq_debug_set_streamk(int mode) { pq::g_sk_mode = mode; }
+extern "C" void pq_debug_set_staged(int on) { pq::g_force_staged = on; }
 // device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
 extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline = dev_buf; }

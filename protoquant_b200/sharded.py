@@ -9,8 +9,8 @@ The gather is the path's only exchange step.  Two implementations:
 
 * fused (default on CUDA when torch's symmetric memory can be set up): every rank owns a
   symmetric [tokens, N] output buffer; the GEMM epilogue stores each finished tile straight
-  into ALL ranks' buffers -- one store to the NVSwitch multicast address when the fabric
-  supports it, else one NVLink peer store per rank -- so the transfer overlaps the MMAs tile
+  into ALL ranks' buffers -- one coalesced NVLink peer store per rank (or, opt-in with
+  PQ_USE_MULTICAST=1, a single store to the NVSwitch multicast address) -- so the transfer overlaps the MMAs tile
   by tile and no separate collective or layout-fixing copy runs.  One symmetric-memory barrier
   follows the kernel.  Output buffers are double-buffered: the tensor returned by forward() is
   valid until the next-but-one forward() of the same module.
@@ -115,7 +115,9 @@ class ShardedDynamicQuantLinear(nn.Module):
         ld = self.world * self.per
         off = self.rank * self.per * esz
         mc = int(getattr(h, "multicast_ptr", 0) or 0) if getattr(h, "has_multicast_support", False) else 0
-        if mc and not os.environ.get("PQ_NO_MULTICAST"):
+        # Measured on 2 x B200 (profiles/README_r1.md): per-peer NVLink stores 0.22 ms vs one store to the
+        # NVSwitch multicast address 0.90 ms for the 2048 x 28672 output, so multicast is opt-in.
+        if mc and os.environ.get("PQ_USE_MULTICAST"):
             dests = [mc + off]
         else:
             dests = [int(p) + off for p in h.buffer_ptrs]

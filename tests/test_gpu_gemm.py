@@ -24,6 +24,7 @@ def _reset_cfg():
     yield
     pq.lib().pq_debug_set_gemm_config(-1)
     pq.lib().pq_debug_set_streamk(-1)
+    pq.lib().pq_debug_set_staged(0)
 
 
 def rand_i8(shape, seed):
@@ -193,3 +194,39 @@ def test_unaligned_operands_are_repacked_by_python_and_rejected_by_c_abi():
 
 def test_empty_gemm():
     assert pq.qgemm_i32(torch.empty(0, 64, dtype=torch.int8, device="cuda"), rand_i8((8, 64), 1).cuda()).shape == (0, 8)
+
+
+@pytest.mark.parametrize("out", [(torch.bfloat16, "bf16"), (torch.float16, "f16"), (torch.float32, "f32")])
+@pytest.mark.parametrize("shape,use_bias", [((256, 512, 512), True), ((100, 264, 272), False), ((16, 4096, 4096), True),
+                                            ((700, 1000, 768), True), ((2048, 3584, 8192), True), ((130, 250, 144), True)])
+def test_staged_coalesced_epilogue_bit_exact(out, shape, use_bias):
+    """The shared-memory staged epilogue used for NVLink peer / multicast destinations."""
+    M, N, K = shape
+    dt, name = out
+    pq.lib().pq_debug_set_staged(1)
+    g = torch.Generator().manual_seed(31)
+    xq, wq = rand_i8((M, K), 32), rand_i8((N, K), 33)
+    s_x = torch.rand(M, generator=g) * 0.1 + 1e-3
+    s_w = torch.rand(N, generator=g) * 0.01 + 1e-4
+    bias = torch.randn(N, generator=g) if use_bias else None
+    y = pq.qgemm(xq.cuda(), s_x.cuda(), wq.cuda(), s_w.cuda(), bias.cuda() if use_bias else None, dt)
+    ref = O.cast_out(O.dequant_epilogue(O.int_mm(xq.numpy(), wq.numpy()), s_x.numpy(), s_w.numpy(),
+                                        bias.numpy() if use_bias else None), name)
+    assert torch.equal(_bits(y.cpu()), _bits(ref))
+
+
+def test_qgemm_multi_writes_every_destination_slice():
+    """pq_qgemm_multi on one GPU: three full-width buffers each receive this shard's column slice."""
+    from protoquant_b200 import functional as F
+    M, N, K, N_total, off = 300, 512, 256, 1536, 512
+    g = torch.Generator().manual_seed(41)
+    xq, wq = rand_i8((M, K), 42).cuda(), rand_i8((N, K), 43).cuda()
+    s_x = (torch.rand(M, generator=g) * 0.1 + 1e-3).cuda()
+    s_w = (torch.rand(N, generator=g) * 0.01 + 1e-4).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = pq.qgemm(xq, s_x, wq, s_w, bias, torch.bfloat16)
+    bufs = [torch.zeros(M, N_total, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    F.qgemm_multi(xq, s_x, wq, s_w, bias, [b.data_ptr() + off * 2 for b in bufs], N_total, torch.bfloat16)
+    for b in bufs:
+        assert torch.equal(b[:, off:off + N], ref)
+        assert not b[:, :off].any() and not b[:, off + N:].any()
