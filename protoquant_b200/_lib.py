@@ -66,6 +66,9 @@ def _declare(lib):
     lib.pq_linear_forward_host.argtypes = [vp, vp, vp, i64]
     lib.pq_linear_destroy.restype = None
     lib.pq_linear_destroy.argtypes = [vp]
+    if hasattr(lib, "pq_debug_set_quant_config"):
+        lib.pq_debug_set_quant_config.restype = None
+        lib.pq_debug_set_quant_config.argtypes = [i32, i32]
     if hasattr(lib, "pq_debug_set_timeline"):
         lib.pq_debug_set_timeline.restype = None
         lib.pq_debug_set_timeline.argtypes = [vp]

@@ -1,0 +1,304 @@
+// Small-M (decode) int8 GEMM + fused dequant epilogue, M <= 128 tokens (SURVEY.md §8 rows a3+a4,
+// "qgemv_i8_smallM").  HBM-bound: the job is to stream Wq[N,K] once at full bandwidth.
+//
+// Swap-AB: the weight tile is the MMA's M operand (128 output channels = 128 TMEM lanes) and the
+// token block is the N operand (M_pad = 16/32/64/128 columns), so a CTA's ring slot is 16 KB of
+// weights + only M_pad*128 B of activations -- 10 slots (180 KB) in flight per SM at M_pad = 16.
+//
+//   grid    = ceil(N/128) channel tiles  x  S K-splits, launched as clusters of S CTAs
+//   per CTA : warp 0 TMA producer, warp 1 tcgen05.mma issuer (M=128, N=M_pad, K=32),
+//             warp 2 TMEM alloc, warps 4-7 dump the int32 accumulator TMEM -> shared memory
+//   reduce  : cluster barrier, then CTA r of the cluster sums channel slice r of all S partials
+//             through distributed shared memory (exact: int32), applies
+//             ((float(acc)*s_x[m])*s_w[n])+bias[n] and stores its slice of y.
+// S is chosen so that tiles x S covers the SMs (N=4096 -> 32 tiles x 4).
+#include "gemm_common.cuh"
+
+namespace pq {
+namespace {
+
+using namespace ptx;
+using namespace gemm;
+
+constexpr int SM_THREADS = 256;
+constexpr int TILE_N = 128;   // output channels per CTA
+
+struct SmallArgs {
+  int M, N, K;
+  int num_kb;       // ceil(K / 128)
+  int splits;       // S = cluster size
+  const float* s_x;
+  const float* s_w;
+  const float* bias;
+  void* out;
+  long long ldo;
+};
+
+template <int MP, int STAGES>
+struct SmallLayout {
+  static constexpr int W_STAGE = TILE_N * BLOCK_K;       // 16 KB
+  static constexpr int X_STAGE = MP * BLOCK_K;
+  static constexpr int X_STAGE_AL = (X_STAGE + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = W_STAGE + X_STAGE;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_X = OFF_W + STAGES * W_STAGE;
+  static constexpr int OFF_PART = OFF_X + STAGES * X_STAGE_AL;    // [MP][128] int32
+  static constexpr int OFF_BAR = OFF_PART + MP * TILE_N * 4;       // full[S], empty[S], tfull
+  static constexpr int OFF_TMEM_PTR = OFF_BAR + (2 * STAGES + 1) * 8;
+  static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ int ld_dsmem_s32(uint32_t local_addr, uint32_t cta) {
+  int v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+      "ld.shared::cluster.s32 %0, [ra];\n\t}"
+      : "=r"(v)
+      : "r"(local_addr), "r"(cta)
+      : "memory");
+  return v;
+}
+
+template <typename OutT> __device__ __forceinline__ void store_one(void* out, long long idx, float f, int raw);
+template <> __device__ __forceinline__ void store_one<__nv_bfloat16>(void* out, long long idx, float f, int) {
+  reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(f);
+}
+template <> __device__ __forceinline__ void store_one<__half>(void* out, long long idx, float f, int) {
+  reinterpret_cast<__half*>(out)[idx] = __float2half_rn(f);
+}
+template <> __device__ __forceinline__ void store_one<float>(void* out, long long idx, float f, int) {
+  reinterpret_cast<float*>(out)[idx] = f;
+}
+template <> __device__ __forceinline__ void store_one<int32_t>(void* out, long long idx, float, int raw) {
+  reinterpret_cast<int32_t*>(out)[idx] = raw;
+}
+
+template <int MP, int STAGES, typename OutT>
+__global__ void __launch_bounds__(SM_THREADS, 1)
+qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_x, const SmallArgs g) {
+  using L = SmallLayout<MP, STAGES>;
+  constexpr bool RAW = std::is_same<OutT, int32_t>::value;
+  constexpr uint32_t TMEM_COLS = MP < 32 ? 32 : MP;
+  constexpr uint32_t idesc = make_idesc(TILE_N, MP);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int S = g.splits;
+  const uint32_t split = (S > 1) ? cluster_ctarank() : 0u;
+  const int n_tile = blockIdx.x / S;
+  const int kb_begin = (int)((long long)g.num_kb * split / S);
+  const int kb_end = (int)((long long)g.num_kb * (split + 1) / S);
+
+  const uint32_t bar_full = smem_base + L::OFF_BAR;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t tmem_ptr_smem = smem_base + L::OFF_TMEM_PTR;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::OFF_TMEM_PTR);
+  int32_t* part = reinterpret_cast<int32_t*>(smem_gen + L::OFF_PART);
+
+  griddep_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + i * 8, 1);
+      mbar_init(bar_empty + i * 8, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(bar_empty + stage * 8, phase ^ 1);
+        const uint32_t fb = bar_full + stage * 8;
+        mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
+        tma_load_2d(smem_base + L::OFF_W + stage * L::W_STAGE, &tmap_w, fb, kb * BLOCK_K, n_tile * TILE_N);
+        tma_load_2d(smem_base + L::OFF_X + stage * L::X_STAGE_AL, &tmap_x, fb, kb * BLOCK_K, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(bar_full + stage * 8, phase);
+        tc_fence_after();
+        const uint64_t wdesc = make_smem_desc(smem_base + L::OFF_W + stage * L::W_STAGE);
+        const uint64_t xdesc = make_smem_desc(smem_base + L::OFF_X + stage * L::X_STAGE_AL);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          mma_i8<1>(tmem_base, wdesc + (uint64_t)(k * (UMMA_K >> 4)), xdesc + (uint64_t)(k * (UMMA_K >> 4)),
+                    idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+        tc_commit<1>(bar_empty + stage * 8);
+        if (kb == kb_end - 1) tc_commit<1>(bar_tfull);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // dump the accumulator: lane n of TMEM holds channel n, column m holds token m
+    const int ew = warp & 3;
+    const int n_local = ew * 32 + (int)lane;
+    if (kb_end > kb_begin) {
+      mbar_wait(bar_tfull, 0);
+      tc_fence_after();
+      __syncwarp();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+      if constexpr (MP == 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(taddr, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) part[m * TILE_N + n_local] = (int32_t)r[m];
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < MP / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int m = 0; m < 32; ++m) part[(c * 32 + m) * TILE_N + n_local] = (int32_t)r[m];
+        }
+      }
+    } else {
+      for (int m = 0; m < MP; ++m) part[m * TILE_N + n_local] = 0;   // empty K range (S > num_kb)
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if (S > 1) cluster_sync(); else __syncthreads();
+
+  // ---- reduce channel slice `split` of every partial and write y ----
+  {
+    const int slice = TILE_N / S;                       // channels this CTA finalises
+    const int total = g.M * slice;
+    const uint32_t part_addr = smem_base + L::OFF_PART;
+    for (int idx = threadIdx.x; idx < total; idx += SM_THREADS) {
+      const int m = idx / slice;
+      const int nl = (int)split * slice + (idx - m * slice);
+      const int n = n_tile * TILE_N + nl;
+      if (n >= g.N) continue;
+      int acc = 0;
+      if (S > 1) {
+        for (int p = 0; p < S; ++p) acc += ld_dsmem_s32(part_addr + (uint32_t)(m * TILE_N + nl) * 4u, (uint32_t)p);
+      } else {
+        acc = part[m * TILE_N + nl];
+      }
+      float v = 0.f;
+      if constexpr (!RAW) {
+        v = __int2float_rn(acc);
+        v = __fmul_rn(v, __ldg(g.s_x + m));
+        v = __fmul_rn(v, __ldg(g.s_w + n));
+        if (g.bias != nullptr) v = __fadd_rn(v, __ldg(g.bias + n));   // no add at all without bias (-0.0 stays -0.0)
+      }
+      store_one<OutT>(g.out, (long long)m * g.ldo + n, v, acc);
+    }
+  }
+
+  if (S > 1) cluster_sync(); else __syncthreads();   // peers may still be reading our partial
+  if (warp == 2) tmem_dealloc<1>(tmem_base, TMEM_COLS);
+}
+
+template <int MP, int STAGES, typename OutT>
+int launch_small(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, SmallArgs g, int num_sms,
+                 cudaStream_t st) {
+  using L = SmallLayout<MP, STAGES>;
+  CUtensorMap tw, tx;
+  int rc = make_tmap(&tw, b, g.N, g.K, ldb, TILE_N);
+  if (rc) return rc;
+  rc = make_tmap(&tx, a, g.M, g.K, lda, MP);
+  if (rc) return rc;
+  auto kern = qgemm_smallm_kernel<MP, STAGES, OutT>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+  });
+  if (attr_err != cudaSuccess)
+    PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));
+  const int n_tiles = (g.N + TILE_N - 1) / TILE_N;
+  int S = 1;
+  while (S < 8 && n_tiles * S * 2 <= num_sms && g.num_kb / (S * 2) >= 2) S *= 2;
+  g.splits = S;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_tiles * S), 1, 1);
+  cfg.blockDim = dim3(SM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = S;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = g_pdl ? 2 : 1;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, tx, g));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return PQ_OK;
+}
+
+template <typename OutT>
+int launch_small_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const SmallArgs& g,
+                       int num_sms, cudaStream_t st) {
+  if (g.M <= 16) return launch_small<16, 10, OutT>(a, lda, b, ldb, g, num_sms, st);
+  if (g.M <= 32) return launch_small<32, 8, OutT>(a, lda, b, ldb, g, num_sms, st);
+  if (g.M <= 64) return launch_small<64, 6, OutT>(a, lda, b, ldb, g, num_sms, st);
+  return launch_small<128, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
+}
+
+}  // namespace
+
+int launch_qgemm_smallm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
+                        const float* s_x, const float* s_w, const float* bias,
+                        void* out, int out_dtype, int64_t ldo,
+                        int64_t M, int64_t N, int64_t K, int num_sms, cudaStream_t stream) {
+  if (M < 1 || M > 128) PQ_FAIL(PQ_ERR_ARG, "small-M GEMM needs 1 <= M <= 128");
+  SmallArgs g = {};
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.num_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  g.s_x = s_x; g.s_w = s_w; g.bias = bias;
+  g.out = out; g.ldo = ldo;
+  switch (out_dtype) {
+    case PQ_BF16: return launch_small_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
+    case PQ_F16: return launch_small_typed<__half>(a, lda, b, ldb, g, num_sms, stream);
+    case PQ_F32: return launch_small_typed<float>(a, lda, b, ldb, g, num_sms, stream);
+    case PQ_I32: return launch_small_typed<int32_t>(a, lda, b, ldb, g, num_sms, stream);
+    default: PQ_FAIL(PQ_ERR_ARG, "small-M GEMM: unsupported output dtype %d", out_dtype);
+  }
+}
+
+}  // namespace pq

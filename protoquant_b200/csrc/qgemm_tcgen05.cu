@@ -21,22 +21,19 @@
 // CG == 2 runs the same roles on a 2-CTA cluster with `cta_group::2`: the pair shares a
 // 256 x BLOCK_N tile, each CTA stages its own 128 rows of A and its half of B, the even
 // CTA issues the MMAs for both and multicasts the commits.
-#include "common.cuh"
-#include "ptx.cuh"
-
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#include <mutex>
-#include <type_traits>
+#include "gemm_common.cuh"
 
 namespace pq {
+int launch_qgemm_smallm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
+                        const float* s_x, const float* s_w, const float* bias,
+                        void* out, int out_dtype, int64_t ldo,
+                        int64_t M, int64_t N, int64_t K, int num_sms, cudaStream_t stream);
 namespace {
 
 using namespace ptx;
+using namespace gemm;
 
 constexpr int BLOCK_M = 128;   // rows of A per CTA (= TMEM lanes)
-constexpr int BLOCK_K = 128;   // bytes (= int8 elements) per ring slot: one 128B swizzle atom
-constexpr int UMMA_K = 32;     // int8 elements per tcgen05.mma
 constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;   // two warps per TMEM lane quarter, each takes half of the columns
@@ -58,25 +55,6 @@ struct GemmArgs {
   unsigned long long* tl;   // debug timeline (32 x u64 per CTA) or null
 };
 
-// ---- descriptors -----------------------------------------------------------------
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows are 128 B apart,
-// 8-row core groups are 1024 B apart (SBO); LBO is unused for swizzled K-major.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
-  d |= (uint64_t)0 << 16;                          // leading byte offset [16,30)
-  d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset  [32,46)
-  d |= (uint64_t)1 << 46;                          // descriptor version 1 (sm_100)
-  d |= (uint64_t)2 << 61;                          // layout: SWIZZLE_128B
-  return d;
-}
-// Instruction descriptor for kind::i8: D = S32, A = B = signed 8-bit, both K-major, no
-// saturation (accumulators must match an exact int32 reference).
-__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) |
-         ((uint32_t)(umma_m >> 4) << 24);
-}
-
 template <int CG, int BN, int STAGES, bool STAGED = false>
 struct SmemLayout {
   static constexpr int A_STAGE = BLOCK_M * BLOCK_K;
@@ -96,38 +74,6 @@ struct SmemLayout {
   static constexpr int TOTAL = OFF_TMEM_PTR + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
-};
-
-template <typename OutT> struct OutPack;
-template <> struct OutPack<__nv_bfloat16> {
-  static constexpr int WORDS = 16;
-  __device__ static __forceinline__ void pack(const float* f, uint32_t* o) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      o[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-  }
-  __device__ static __forceinline__ __nv_bfloat16 one(float f) { return __float2bfloat16_rn(f); }
-};
-template <> struct OutPack<__half> {
-  static constexpr int WORDS = 16;
-  __device__ static __forceinline__ void pack(const float* f, uint32_t* o) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-      o[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-  }
-  __device__ static __forceinline__ __half one(float f) { return __float2half_rn(f); }
-};
-template <> struct OutPack<float> {
-  static constexpr int WORDS = 32;
-  __device__ static __forceinline__ void pack(const float* f, uint32_t* o) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(f[i]);
-  }
-  __device__ static __forceinline__ float one(float f) { return f; }
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -364,6 +310,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int etid = (int)threadIdx.x - EPI_WARP0 * 32;   // 0..255
     constexpr int CH = BN / 64;                  // 32-column chunks per warp
     const int c_lo = half * CH, c_hi = c_lo + CH;
+    const bool has_bias = g.bias != nullptr;   // without bias there is no add at all (-0.0 stays -0.0)
     int iter = 0;
     int tile, kb0, kb1;
     for (; sched.next(tile, kb0, kb1); ++iter) {
@@ -487,7 +434,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 float v = __int2float_rn((int)r[4 * j4 + j]);
                 v = __fmul_rn(v, sx);
                 v = __fmul_rn(v, wv[j]);
-                v = __fadd_rn(v, bv[j]);
+                if (has_bias) v = __fadd_rn(v, bv[j]);
                 f[4 * j4 + j] = v;
               }
             }
@@ -582,7 +529,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 float v = __int2float_rn((int)r[4 * j4 + j]);
                 v = __fmul_rn(v, sx);
                 v = __fmul_rn(v, wv[j]);
-                v = __fadd_rn(v, bv[j]);
+                if (has_bias) v = __fadd_rn(v, bv[j]);
                 f[4 * j4 + j] = v;
               }
             }
@@ -620,35 +567,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   if (threadIdx.x == 0) PQ_TL(7);
-}
-
-// ---- host side ---------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  });
-  return fn;
-}
-
-// [rows, kbytes] int8 matrix, row stride `ld` bytes -> boxes of [box_rows x 128 B], 128B swizzle
-int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t kbytes, int64_t ld, int box_rows) {
-  auto fn = get_encode_fn();
-  if (!fn) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return PQ_OK;
 }
 
 // ---- stream-K workspace pool ----------------------------------------------------------
@@ -833,6 +751,10 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   int num_sms = 0;
   int rc = check_device(&num_sms);
   if (rc) return rc;
+  // Decode-sized batches take the swap-AB weight-streaming kernel (qgemm_smallm.cu).
+  if (M <= 128 && n_out == 1 && !g_force_staged && g_sk_mode != 1 && (g_force_cfg < 0 || g_force_cfg == 7))
+    return launch_qgemm_smallm(a, lda, b, ldb, s_x, s_w, bias, outs[0], out_dtype, ldo, M, N, K, num_sms, stream);
+  if (g_force_cfg == 7) PQ_FAIL(PQ_ERR_ARG, "qgemm: config 7 (small-M kernel) needs M <= 128");
   GemmArgs g = {};
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.s_x = s_x; g.s_w = s_w; g.bias = bias;

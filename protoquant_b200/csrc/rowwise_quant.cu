@@ -25,6 +25,7 @@
 #include <type_traits>
 
 namespace pq {
+int g_force_tpr = 0, g_force_vpt = 0;   // test hook (pq_debug_set_quant_config)
 namespace {
 
 template <typename... KArgs, typename... Args>
@@ -385,15 +386,33 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
     return PQ_OK;
   }
   const int nvec = (int)(K / EPV);
-#define PQ_LAUNCH(TPR, VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st)
-  if (nvec <= 32 * 4) PQ_LAUNCH(32, 4);
-  if (nvec <= 64 * 4) PQ_LAUNCH(64, 4);
-  if (nvec <= 128 * 4) PQ_LAUNCH(128, 4);
-  if (nvec <= 256 * 4) PQ_LAUNCH(256, 4);
-  if (nvec <= 512 * 4) PQ_LAUNCH(512, 4);
-  if (nvec <= 1024 * 4) PQ_LAUNCH(1024, 4);
-  PQ_LAUNCH(1024, 8);
-#undef PQ_LAUNCH
+  // Pick (threads per row, vectors per thread): cover the row with as few idle lanes as possible,
+  // preferring small thread groups (more rows in flight per SM) and <= 6 vectors per thread.
+  static const int kVpt[5] = {4, 3, 6, 2, 8};
+  int best_tpr = 1024, best_vpt = 8;
+  double best_score = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    const int vpt = kVpt[i];
+    int tpr = 32;
+    while (tpr < 1024 && tpr * vpt < nvec) tpr *= 2;
+    if (tpr * vpt < nvec) continue;
+    double score = (double)(tpr * vpt - nvec) / (double)(tpr * vpt);   // idle-lane fraction
+    // measured on B200 (tools/sweep_quant.sh): 1024-thread groups lose ~35% (one row per CTA, two
+    // CTAs per SM); with many rows, more bytes in flight per thread wins (64x8 beats 128x4 by 5%).
+    if (vpt == 2) score += 0.03;
+    if (tpr >= 512) score += 0.04;
+    if (tpr == 1024) score += 0.20;
+    if (M >= 16384) score -= (vpt == 8 ? 0.02 : vpt == 6 ? 0.01 : 0.0);
+    else if (vpt == 8) score += 0.03;
+    if (score < best_score) { best_score = score; best_tpr = tpr; best_vpt = vpt; }
+  }
+  if (g_force_tpr > 0 && g_force_vpt > 0 && g_force_tpr * g_force_vpt >= nvec) { best_tpr = g_force_tpr; best_vpt = g_force_vpt; }
+#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st);
+#define PQ_CASE_T(TPR) PQ_CASE_V(TPR, 2) PQ_CASE_V(TPR, 3) PQ_CASE_V(TPR, 4) PQ_CASE_V(TPR, 6) PQ_CASE_V(TPR, 8)
+  PQ_CASE_T(32) PQ_CASE_T(64) PQ_CASE_T(128) PQ_CASE_T(256) PQ_CASE_T(512) PQ_CASE_T(1024)
+#undef PQ_CASE_T
+#undef PQ_CASE_V
+  PQ_FAIL(PQ_ERR_ARG, "rowwise quant: no kernel configuration for %d vectors per row", nvec);
 }
 
 }  // namespace
@@ -419,3 +438,6 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
 }
 
 }  // namespace pq
+
+// Test/bench hook: force (threads per row, 16-byte vectors per thread) of the vectorised kernel; 0,0 = heuristic.
+extern "C" void pq_debug_set_quant_config(int tpr, int vpt) { pq::g_force_tpr = tpr; pq::g_force_vpt = vpt; }

@@ -16,7 +16,7 @@ import protoquant_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = [-1, 0, 1, 2, 3, 4]   # -1 = heuristic; see launch_typed() in csrc/qgemm_tcgen05.cu
+CONFIGS = [-1, 0, 1, 2, 3, 4]   # -1 = heuristic (small-M kernel for M <= 128); see launch_typed() in csrc/qgemm_tcgen05.cu
 
 
 @pytest.fixture(autouse=True)
@@ -230,3 +230,28 @@ def test_qgemm_multi_writes_every_destination_slice():
     for b in bufs:
         assert torch.equal(b[:, off:off + N], ref)
         assert not b[:, :off].any() and not b[:, off + N:].any()
+
+
+@pytest.mark.parametrize("shape", [(1, 4096, 4096), (2, 4096, 4096), (7, 11008, 4096), (16, 4096, 11008), (17, 768, 3072),
+                                   (31, 3072, 768), (33, 1000, 144), (64, 4096, 4096), (65, 8192, 8192), (100, 264, 272),
+                                   (128, 28672, 8192), (128, 8192, 28672), (5, 8, 16), (16, 136, 4096)])
+def test_small_m_kernel_int32_and_epilogue(shape):
+    """Decode path (swap-AB, K split across a cluster, DSMEM reduction): exact accumulators and
+    bit-exact fused epilogue for every M_pad bucket, ragged N/K, 1..8 K-splits."""
+    M, N, K = shape
+    pq.lib().pq_debug_set_gemm_config(7)
+    g = torch.Generator().manual_seed(51)
+    xq, wq = rand_i8((M, K), 52), rand_i8((N, K), 53)
+    acc = pq.qgemm_i32(xq.cuda(), wq.cuda())
+    ref = cpu_int_mm(xq, wq)
+    assert torch.equal(acc.cpu(), ref)
+    s_x = torch.rand(M, generator=g) * 0.1 + 1e-3
+    s_w = torch.rand(N, generator=g) * 0.01 + 1e-4
+    bias = torch.randn(N, generator=g)
+    for dt, name in ((torch.bfloat16, "bf16"), (torch.float16, "f16"), (torch.float32, "f32")):
+        y = pq.qgemm(xq.cuda(), s_x.cuda(), wq.cuda(), s_w.cuda(), bias.cuda(), dt)
+        want = O.cast_out(O.dequant_epilogue(ref.numpy(), s_x.numpy(), s_w.numpy(), bias.numpy()), name)
+        assert torch.equal(_bits(y.cpu()), _bits(want))
+    y = pq.qgemm(xq.cuda(), s_x.cuda(), wq.cuda(), s_w.cuda(), None, torch.bfloat16)
+    want = O.cast_out(O.dequant_epilogue(ref.numpy(), s_x.numpy(), s_w.numpy(), None), "bf16")
+    assert torch.equal(_bits(y.cpu()), _bits(want))
