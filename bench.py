@@ -398,6 +398,12 @@ def run_ours(args):
     except Exception as ex:  # never let the side measurement kill the headline line
         sharded = {"error": repr(ex)[:200]}
 
+    decode = None
+    if rank == 0:
+        try:
+            decode = decode_leg(pq, F, torch, dev, peaks)
+        except Exception as ex:
+            decode = {"error": repr(ex)[:200]}
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1) else None
     clocks = sampler.result()
     if rank == 0:
@@ -412,13 +418,60 @@ def run_ours(args):
             "tokens_per_s": world * M_TOKENS / (ms_per_step * 1e-3),
             "frac_of_nominal_int8": value / world / NOMINAL_INT8_TOPS,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "sharded_70b": sharded,
+            "clocks": clocks, "sharded_70b": sharded, "decode_16tok": decode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def decode_leg(pq, F, torch, dev, peaks):
+    """BASELINE.json configs[0]: one nn.Linear 4096x4096 on 16 tokens (plus the Llama-7B MLP shapes at 16
+    tokens).  HBM-bound weight streaming: achieved = int8 weight bytes / time, from a CUDA-graph replay of
+    the module forward (act-quant + small-M tcgen05 GEMM) cycling 8 distinct weight sets (> L2)."""
+    res = {}
+    for name, K, N in (("linear_4096x4096", 4096, 4096), ("gate_4096x11008", 4096, 11008), ("down_11008x4096", 11008, 4096)):
+        nset = 8
+        mods = []
+        for i in range(nset):
+            m = pq.DynamicQuantLinear(K, N, bias=True, device=dev)
+            m.qweight_storage.random_(-127, 128)
+            m.weight_scale.uniform_(1e-4, 1e-3)
+            mods.append(m)
+        x = torch.randn(16, K, device=dev).to(torch.bfloat16)
+        ws = (F.alloc_q(16, K, dev), torch.empty(16, dtype=torch.float32, device=dev))
+        y = torch.empty(16, N, dtype=torch.bfloat16, device=dev)
+
+        def run():
+            for m in mods:
+                xq, sx = F.quantize_act(x, out=ws)
+                F.qgemm(xq, sx, m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=y)
+        run()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run()
+        for _ in range(3):
+            g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / (20 * nset)
+        gbs = (N * K + 16 * K * 3 + 16 * N * 2) / (us * 1e-6) / 1e9
+        res[name] = {"us_per_forward": us, "tokens_per_s": 16 / (us * 1e-6), "achieved_gbs": gbs,
+                     "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+        del mods
+    return res
 
 
 def sharded_leg(pq, torch, dist, dev, rank, world):

@@ -1,9 +1,10 @@
-// Small-M (decode) int8 GEMM + fused dequant epilogue, M <= 128 tokens (SURVEY.md §8 rows a3+a4,
+// Small-M (decode) int8 GEMM + fused dequant epilogue, M <= 64 tokens (SURVEY.md §8 rows a3+a4,
 // "qgemv_i8_smallM").  HBM-bound: the job is to stream Wq[N,K] once at full bandwidth.
 //
 // Swap-AB: the weight tile is the MMA's M operand (128 output channels = 128 TMEM lanes) and the
-// token block is the N operand (M_pad = 16/32/64/128 columns), so a CTA's ring slot is 16 KB of
-// weights + only M_pad*128 B of activations -- 10 slots (180 KB) in flight per SM at M_pad = 16.
+// token block is the N operand (M_pad = 16/32/64 columns), so a CTA's ring slot is 16 KB of
+// weights + only M_pad*128 B of activations; two CTAs share an SM (<= 104 KB each), which keeps
+// ~180 KB of weight loads in flight per SM.
 //
 //   grid    = ceil(N/128) channel tiles  x  S K-splits, launched as clusters of S CTAs
 //   per CTA : warp 0 TMA producer, warp 1 tcgen05.mma issuer (M=128, N=M_pad, K=32),
@@ -47,7 +48,7 @@ struct SmallLayout {
   static constexpr int OFF_TMEM_PTR = OFF_BAR + (2 * STAGES + 1) * 8;
   static constexpr int TOTAL = OFF_TMEM_PTR + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
-  static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(DYN_BYTES <= 113 * 1024, "two CTAs must fit per SM");
 };
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -87,7 +88,7 @@ template <> __device__ __forceinline__ void store_one<int32_t>(void* out, long l
 }
 
 template <int MP, int STAGES, typename OutT>
-__global__ void __launch_bounds__(SM_THREADS, 1)
+__global__ void __launch_bounds__(SM_THREADS, 2)
 qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_x, const SmallArgs g) {
   using L = SmallLayout<MP, STAGES>;
@@ -249,8 +250,10 @@ int launch_small(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, Sma
   if (attr_err != cudaSuccess)
     PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));
   const int n_tiles = (g.N + TILE_N - 1) / TILE_N;
+  // Two CTAs fit per SM (<= 113 KB of shared memory each): split K until the grid fills those
+  // 2 x num_sms slots, keeping at least 4 K blocks per CTA.
   int S = 1;
-  while (S < 8 && n_tiles * S * 2 <= num_sms && g.num_kb / (S * 2) >= 2) S *= 2;
+  while (S < 8 && n_tiles * S * 2 <= 2 * num_sms && g.num_kb / (S * 2) >= 4) S *= 2;
   g.splits = S;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_tiles * S), 1, 1);
@@ -274,10 +277,9 @@ int launch_small(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, Sma
 template <typename OutT>
 int launch_small_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const SmallArgs& g,
                        int num_sms, cudaStream_t st) {
-  if (g.M <= 16) return launch_small<16, 10, OutT>(a, lda, b, ldb, g, num_sms, st);
-  if (g.M <= 32) return launch_small<32, 8, OutT>(a, lda, b, ldb, g, num_sms, st);
-  if (g.M <= 64) return launch_small<64, 6, OutT>(a, lda, b, ldb, g, num_sms, st);
-  return launch_small<128, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
+  if (g.M <= 16) return launch_small<16, 5, OutT>(a, lda, b, ldb, g, num_sms, st);   //  98 KB smem
+  if (g.M <= 32) return launch_small<32, 4, OutT>(a, lda, b, ldb, g, num_sms, st);   //  96 KB
+  return launch_small<64, 3, OutT>(a, lda, b, ldb, g, num_sms, st);                  // 104 KB
 }
 
 }  // namespace
@@ -286,7 +288,7 @@ int launch_qgemm_smallm(const int8_t* a, int64_t lda, const int8_t* b, int64_t l
                         const float* s_x, const float* s_w, const float* bias,
                         void* out, int out_dtype, int64_t ldo,
                         int64_t M, int64_t N, int64_t K, int num_sms, cudaStream_t stream) {
-  if (M < 1 || M > 128) PQ_FAIL(PQ_ERR_ARG, "small-M GEMM needs 1 <= M <= 128");
+  if (M < 1 || M > 64) PQ_FAIL(PQ_ERR_ARG, "small-M GEMM needs 1 <= M <= 64");
   SmallArgs g = {};
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.num_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);

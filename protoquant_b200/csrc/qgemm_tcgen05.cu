@@ -752,9 +752,9 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   int rc = check_device(&num_sms);
   if (rc) return rc;
   // Decode-sized batches take the swap-AB weight-streaming kernel (qgemm_smallm.cu).
-  if (M <= 128 && n_out == 1 && !g_force_staged && g_sk_mode != 1 && (g_force_cfg < 0 || g_force_cfg == 7))
+  if (M <= 64 && n_out == 1 && !g_force_staged && g_sk_mode != 1 && (g_force_cfg < 0 || g_force_cfg == 7))
     return launch_qgemm_smallm(a, lda, b, ldb, s_x, s_w, bias, outs[0], out_dtype, ldo, M, N, K, num_sms, stream);
-  if (g_force_cfg == 7) PQ_FAIL(PQ_ERR_ARG, "qgemm: config 7 (small-M kernel) needs M <= 128");
+  if (g_force_cfg == 7) PQ_FAIL(PQ_ERR_ARG, "qgemm: config 7 (small-M kernel) needs M <= 64");
   GemmArgs g = {};
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.s_x = s_x; g.s_w = s_w; g.bias = bias;
