@@ -290,6 +290,9 @@ def run_ours(args):
     evs = []
     roof_steps = min(args.steps, 50)
     for _ in range(roof_steps):
+        # let the host run ahead (14 launches + 21 event records take ~0.3 ms of CPU time) so that the
+        # per-launch CUDA-event intervals below contain no launch-queue starvation gaps
+        torch.cuda._sleep(2_000_000)
         for name, k, n, src in LINEARS:
             m = mods[name]
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))

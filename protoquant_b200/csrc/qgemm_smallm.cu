@@ -136,12 +136,23 @@ qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
-  griddep_wait();
+  // PDL: the weights do not depend on the previous kernel (the activation quantizer), so the
+  // producer starts streaming them before it waits for that kernel; everyone else waits here.
+  if (!(warp == 0 && lane == 0)) griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int n_pre = (kb_end - kb_begin) < STAGES ? (kb_end - kb_begin) : STAGES;
+      for (int i = 0; i < n_pre; ++i) {      // ring is empty: no `empty` wait needed yet
+        const uint32_t fb = bar_full + i * 8;
+        mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
+        tma_load_2d(smem_base + L::OFF_W + i * L::W_STAGE, &tmap_w, fb, (kb_begin + i) * BLOCK_K, n_tile * TILE_N);
+      }
+      griddep_wait();                          // xq / s_x are produced by the previous kernel
+      for (int i = 0; i < n_pre; ++i)
+        tma_load_2d(smem_base + L::OFF_X + i * L::X_STAGE_AL, &tmap_x, bar_full + i * 8, (kb_begin + i) * BLOCK_K, 0);
+      uint32_t stage = (n_pre == STAGES) ? 0 : (uint32_t)n_pre, phase = (n_pre == STAGES) ? 1 : 0;
+      for (int kb = kb_begin + n_pre; kb < kb_end; ++kb) {
         mbar_wait(bar_empty + stage * 8, phase ^ 1);
         const uint32_t fb = bar_full + stage * 8;
         mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
