@@ -285,29 +285,54 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * OPS_PER_STEP / (ms_per_step * 1e-3) / 1e12
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events on the launch stream ----
-    gemm_ms, quant_ms = 0.0, 0.0
-    evs = []
-    roof_steps = min(args.steps, 50)
-    for _ in range(roof_steps):
-        # let the host run ahead (14 launches + 21 event records take ~0.3 ms of CPU time) so that the
-        # per-launch CUDA-event intervals below contain no launch-queue starvation gaps
-        torch.cuda._sleep(2_000_000)
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM) ----
+    # Average launch duration = CUDA-event time of a graph that replays ONLY the step's seven GEMM
+    # launches (same weights cycling through 202 MB, pre-quantised activations), divided by the
+    # launch count; a second graph does the same for the seven act-quant launches.  (Bracketing every
+    # launch with its own pair of events inflates a 30-70 us kernel by ~10 us of event latency.)
+    for name, k, n, src in LINEARS:
+        F.quantize_act(acts[src], out=xq_ws[src])
+
+    def gemm_only():
         for name, k, n, src in LINEARS:
             m = mods[name]
-            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            a.record()
-            xq, sx = F.quantize_act(acts[src], out=xq_ws[src])
-            b.record()
-            F.qgemm(xq, sx, m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
-            c.record()
-            evs.append((a, b, c, k, n))
-    torch.cuda.synchronize()
-    quant_bytes = 0
-    for a, b, c, k, n in evs:
-        quant_ms += a.elapsed_time(b)
-        gemm_ms += b.elapsed_time(c)
-        quant_bytes += M_TOKENS * (3 * k + 4)
+            F.qgemm(xq_ws[src][0], xq_ws[src][1], m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
+
+    def quant_only():
+        for name, k, n, src in LINEARS:
+            F.quantize_act(acts[src], out=xq_ws[src])
+
+    def time_graph(fn, reps):
+        fn()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        run = fn
+        if not args.no_graph:
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    fn()
+                run = gr.replay
+            except Exception:
+                torch.cuda.synchronize()
+        for _ in range(3):
+            run()
+        t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_a.record()
+        for _ in range(reps):
+            run()
+        t_b.record()
+        torch.cuda.synchronize()
+        return t_a.elapsed_time(t_b)
+
+    roof_steps = max(3, min(args.steps, 100))
+    gemm_ms = time_graph(gemm_only, roof_steps)
+    quant_ms = time_graph(quant_only, roof_steps)
+    quant_bytes = roof_steps * sum(M_TOKENS * (3 * k + 4) for _, k, n, _ in LINEARS)
     gemm_tops = OPS_PER_STEP * roof_steps / (gemm_ms * 1e-3) / 1e12
     peak_tops = 2.0 * peaks["bf16_tflops"]
     traffic = None
@@ -325,7 +350,8 @@ def run_ours(args):
         "avg_launch_ms": gemm_ms / (roof_steps * len(LINEARS)),
         "act_quant": {"bound": "hbm", "achieved": quant_bytes / (quant_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                       "unit": "GB/s", "frac": quant_bytes / (quant_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                      "note": "config-size inputs (16-45 MB) are L2-resident and launch-latency bound; see act_quant_stream"},
+                      "avg_launch_ms": quant_ms / (roof_steps * len(LINEARS)),
+                      "note": "the step's seven act-quant launches alone (2048 x 4096 / 11008 bf16, 25-68 MB each): latency bound; see act_quant_stream"},
     }
     # HBM-streaming point for the activation quantizer (traffic >> L2): SURVEY.md §8d
     if rank == 0:
@@ -353,35 +379,53 @@ def run_ours(args):
     copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
 
+    # Software-pipelined over steps: device input buffers are double-buffered, so the H2D copies of
+    # step s+1, the kernels of step s and the D2H copies of step s-1 run concurrently (three streams,
+    # events only).  Every byte of every step still crosses PCIe inside the timed region.
+    acts2 = [acts, {a: torch.empty_like(t) for a, t in acts.items()}]
+    compute_done = [None, None]
+    step_no = [0]
+
     def e2e_step():
+        buf = step_no[0] & 1
+        step_no[0] += 1
         ready = {}
         with torch.cuda.stream(copy_in):
+            if compute_done[buf] is not None:
+                copy_in.wait_event(compute_done[buf])      # kernels of step s-2 have consumed this buffer
             for a in ACTS:
-                acts[a].copy_(host_in[a], non_blocking=True)
+                acts2[buf][a].copy_(host_in[a], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_in)
                 ready[a] = ev
         for name, k, n, src in LINEARS:
             main.wait_event(ready[src])
-            y = mods[name](acts[src])                      # public API: the nn.Linear replacement
+            y = mods[name](acts2[buf][src])                # public API: the nn.Linear replacement
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(done)
                 host_out[name].copy_(y, non_blocking=True)
                 y.record_stream(copy_out)
-        main.wait_stream(copy_out)
-        copy_in.wait_stream(main)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        compute_done[buf] = ev
 
-    e2e_steps = max(3, min(args.steps, 30))
+    def e2e_drain():
+        main.wait_stream(copy_out)
+        main.wait_stream(copy_in)
+
+    e2e_steps = max(3, min(args.steps, 60))
     for _ in range(3):
         e2e_step()
+    e2e_drain()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(e2e_steps):
         e2e_step()
+    e2e_drain()                                            # t1 is recorded after the last D2H copy has landed
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)

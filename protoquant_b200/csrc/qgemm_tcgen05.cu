@@ -53,6 +53,7 @@ struct GemmArgs {
   int32_t* sk_ws;     // [workers][2][CG][BN*128] int32 partial sums
   int* sk_flags;      // [workers*CG][2] ticket / done counters (self-cleaning, zero between launches)
   unsigned long long* tl;   // debug timeline (32 x u64 per CTA) or null
+  int prefetch_b;           // 1 = warp 3 prefetches this CTA's weight boxes into L2 ahead of the ring
 };
 
 template <int CG, int BN, int STAGES, bool STAGED = false>
@@ -193,6 +194,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   float* sw_smem = reinterpret_cast<float*>(smem_gen + L::OFF_SW);
   float* bias_smem = reinterpret_cast<float*>(smem_gen + L::OFF_BIAS);
   volatile int* misc_smem = reinterpret_cast<volatile int*>(smem_gen + L::OFF_MISC);
+  volatile int* prod_count = reinterpret_cast<volatile int*>(smem_gen + L::OFF_MISC + 4);   // k-blocks the producer has issued
 
   griddep_launch_dependents();   // PDL: the next kernel may begin its own prologue
   if (warp == 0 && lane == 0) {
@@ -201,6 +203,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     prefetch_tmap(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
+    *prod_count = 0;
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bar_full + i * 8, CG);   // one producer arrive per CTA of the pair (leader's copy is used)
       mbar_init(bar_empty + i * 8, 1);   // one tcgen05.commit
@@ -221,8 +224,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
   // PDL: everything above overlapped the previous kernel's tail; from here on we touch global
-  // memory that kernel may have produced (xq, s_x) or may still be reading (y).
-  griddep_wait();
+  // memory that kernel may have produced (xq, s_x) or may still be reading (y).  The L2
+  // prefetcher only touches the (static) weights, so it does not wait.
+  if (!(warp == 3 && lane == 0)) griddep_wait();
 
   const int num_clusters = gridDim.x / CG;
   const int cluster_id = blockIdx.x / CG;
@@ -256,10 +260,33 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive_remote(fb, 0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          *prod_count = *prod_count + 1;
           if (g.tl && g.tl[(size_t)blockIdx.x * 32 + 2] == 0) PQ_TL(2);
         }
       }
       PQ_TL(3);
+    }
+  } else if (warp == 3) {
+    // ================= L2 prefetcher =================
+    // Experiment, OFF by default (pq_debug_set_prefetch): one thread walks the same schedule up to
+    // PF_AHEAD k-blocks ahead of the producer and pulls this CTA's B boxes into L2, on the theory
+    // that cold weights miss to DRAM for longer than the shared-memory ring can cover.  Measured:
+    // the step gets 6-9 % SLOWER (profiles/README_r1.md) -- the kernel is bound by L2 request
+    // bandwidth, and the redundant prefetches (8 m-blocks share a B box) add to exactly that.
+    if (lane == 0 && g.prefetch_b) {
+      constexpr int PF_AHEAD = 24;
+      int count = 0;
+      int tile, kb0, kb1;
+      Sched pf = sched;
+      while (pf.next(tile, kb0, kb1)) {
+        int m_blk, n_blk;
+        tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
+        const int n_idx = n_blk * BN + (int)cta_rank * L::B_ROWS;
+        for (int kb = kb0; kb < kb1; ++kb, ++count) {
+          while (count - *prod_count > PF_AHEAD) __nanosleep(200);
+          tma_prefetch_l2_2d(&tmap_b, kb * BLOCK_K, n_idx);
+        }
+      }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
@@ -698,6 +725,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
 
 int g_force_cfg = -1;  // test hook: see pq_debug_set_gemm_config
 int g_force_staged = 0;  // test hook: staged epilogue even for a single destination
+int g_prefetch_b = 0;    // L2 prefetch of the weight operand (pq_debug_set_prefetch): measured SLOWER, off
 
 template <typename OutT>
 int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g,
@@ -767,6 +795,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
     if ((uintptr_t)outs[d] & 15) g.vec_ok = 0;
   }
   g.tl = g_timeline;
+  g.prefetch_b = g_prefetch_b;
   switch (out_dtype) {
     case PQ_BF16: return launch_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
     case PQ_F16: return launch_typed<__half>(a, lda, b, ldb, g, num_sms, stream);
@@ -784,5 +813,6 @@ extern "C" void pq_debug_set_gemm_config(int cfg) { pq::g_force_cfg = cfg; }
 // -1 = heuristic, 0 = never use stream-K, 1 = use stream-K whenever it is legal
 extern "C" void pq_debug_set_streamk(int mode) { pq::g_sk_mode = mode; }
 extern "C" void pq_debug_set_staged(int on) { pq::g_force_staged = on; }
+extern "C" void pq_debug_set_prefetch(int on) { pq::g_prefetch_b = on; }
 // device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
 extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline = dev_buf; }

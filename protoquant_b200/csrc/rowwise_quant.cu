@@ -281,17 +281,21 @@ rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int6
   }
 }
 
-// ---- transposed output, tiled: 32 rows per CTA, coalesced both ways ----------------
-// Pass 1 computes the 32 row scales (one warp per 4 rows); pass 2 re-reads the rows
-// (L2 hits: 32 rows were just streamed by this CTA), quantises 32x128 tiles into
-// shared memory and writes them out as 128 runs of 32 contiguous bytes.
-template <typename T>
+// ---- transposed output, tiled: 32 rows per CTA ---------------------------------------
+// Pass 1 computes the 32 row scales (one warp per 4 rows, 16-byte loads when VEC); pass 2
+// re-reads the rows (L2 hits: the CTA just streamed them), quantises 32 x 128 tiles into
+// shared memory row-major and writes them out transposed: each thread gathers 16 codes of
+// one k and stores them with one 16-byte store (32 contiguous bytes per k per CTA).
+// VEC requires 16-byte aligned rows of x and of xq_t and K % (16/sizeof(T)) == 0.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, int64_t ldx,
                                 int8_t* __restrict__ xq_t, int64_t ldq,
                                 float* __restrict__ s_out, int scale_mode, float eps) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr int PITCH = 144;                         // bytes per staged row (16-byte aligned)
   __shared__ RowQ rowq[32];
-  __shared__ int8_t tile[128][33];
+  __shared__ __align__(16) int8_t tile[32 * PITCH];
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -301,7 +305,18 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
     float amax = 0.f;
     if (row < M) {
       const T* xr = x + row * ldx;
-      for (int64_t k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(load_as_float<T>(xr + k)));
+      if (VEC) {
+        const int64_t nvec = K / EPV;
+        if (sizeof(T) == 2) {
+          uint32_t m = 0;
+          for (int64_t v = lane; v < nvec; v += 32) m = absmax_u16x2(ld_stream_16(xr + v * EPV), m);
+          amax = u16_mag_to_float<T>(m);
+        } else {
+          for (int64_t v = lane; v < nvec; v += 32) amax = vec_absmax<float>(ld_stream_16(xr + v * EPV), amax);
+        }
+      } else {
+        for (int64_t k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(load_as_float<T>(xr + k)));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -312,37 +327,59 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
     }
   }
   __syncthreads();
+  const bool rows_full = row0 + 32 <= M;
   for (int64_t k0 = 0; k0 < K; k0 += 128) {
-    // quantise: thread (r = tid/8, c4 = tid%8) handles 16 consecutive k of row r
+    // quantise: thread (r = tid/8, group = tid%8) handles 16 consecutive k of row r
     {
       const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 16;
       const int64_t row = row0 + r;
       const RowQ rq = rowq[r];
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const int64_t k = k0 + c0 + j;
-        int8_t code = 0;
-        if (row < M && k < K) {
-          const float xv = load_as_float<T>(x + row * ldx + k);
-          float m;
-          if (rq.path == 0) m = quant_fast(xv, rq);
-          else if (rq.path == 1) m = quant_div(xv, rq);
-          else m = quant_mul(xv, rq);
-          code = code_of(m);
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = 0.f;
+      if (row < M) {
+        const T* xr = x + row * ldx + k0 + c0;
+        if (VEC) {
+#pragma unroll
+          for (int v = 0; v < 16 / EPV; ++v)
+            if (k0 + c0 + (v + 1) * EPV <= K) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(xr + v * EPV);
+              unpack<T>(raw, f + v * EPV);
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (k0 + c0 + j < K) f[j] = load_as_float<T>(xr + j);
         }
-        tile[c0 + j][r] = code;
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (rq.path == 0) f[j] = quant_fast(f[j], rq);
+        else if (rq.path == 1) f[j] = quant_div(f[j], rq);
+        else f[j] = quant_mul(f[j], rq);
+      }
+      uint4 o;
+      o.x = pack4(f[0], f[1], f[2], f[3]);   o.y = pack4(f[4], f[5], f[6], f[7]);
+      o.z = pack4(f[8], f[9], f[10], f[11]); o.w = pack4(f[12], f[13], f[14], f[15]);
+      *reinterpret_cast<uint4*>(tile + r * PITCH + c0) = o;
     }
     __syncthreads();
-    // write: 128 k-rows x 32 bytes; thread -> (k = tid/2 , half = tid%2) 16 bytes
+    // write: 128 k-rows x 32 bytes; thread -> (k = tid/2, half = tid%2) gathers 16 rows of one k
     {
       const int kk = threadIdx.x >> 1, h = (threadIdx.x & 1) * 16;
       const int64_t k = k0 + kk;
       if (k < K) {
+        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int64_t row = row0 + h + j;
-          if (row < M) xq_t[k * ldq + row] = tile[kk][h + j];
+        for (int j = 0; j < 16; ++j)
+          w[j >> 2] |= (uint32_t)(uint8_t)tile[(h + j) * PITCH + kk] << (8 * (j & 3));
+        int8_t* dst = xq_t + k * ldq + row0 + h;
+        if (VEC && rows_full) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (row0 + h + j < M) dst[j] = (int8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
         }
       }
     }
@@ -370,8 +407,14 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
   if (transpose) {
     const int64_t grid = (M + 31) / 32;
-    PQ_CUDA(launch_pdl(rowwise_quant_transposed_kernel<T>, (unsigned)grid, 256u, st,
-                       (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
+    const bool tvec = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) && ((ldx * (int64_t)sizeof(T)) % 16 == 0) &&
+                      (((uintptr_t)xq & 15) == 0) && (ldq % 16 == 0);
+    if (tvec)
+      PQ_CUDA(launch_pdl(rowwise_quant_transposed_kernel<T, true>, (unsigned)grid, 256u, st,
+                         (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
+    else
+      PQ_CUDA(launch_pdl(rowwise_quant_transposed_kernel<T, false>, (unsigned)grid, 256u, st,
+                         (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return PQ_OK;
   }
