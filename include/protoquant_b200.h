@@ -5,7 +5,7 @@
  * (BASELINE.json north_star).  The reference checkout is ABSENT in this
  * environment (/root/reference holds only CODE_OF_CONDUCT.md),
  * so no reference file:line can be cited; each entry point instead cites the
- * SURVEY.md §8 row it implements.  The Python side (protoquant_b200/*.py) binds
+ * SURVEY.md §8 row it implements.  The Python side (the protoquant_b200 package) binds
  * these symbols with ctypes; INTEGRATION.md shows the stub.
  *
  * Conventions

@@ -282,9 +282,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         int m_blk, n_blk;
         tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
         const int n_idx = n_blk * BN + (int)cta_rank * L::B_ROWS;
+        // mode 1: every CTA prefetches its own boxes; mode 2: one m-block per n-block does it
+        const bool duty = (g.prefetch_b == 1) || (m_blk == n_blk % g.num_m_blocks);
         for (int kb = kb0; kb < kb1; ++kb, ++count) {
           while (count - *prod_count > PF_AHEAD) __nanosleep(200);
-          tma_prefetch_l2_2d(&tmap_b, kb * BLOCK_K, n_idx);
+          if (duty) tma_prefetch_l2_2d(&tmap_b, kb * BLOCK_K, n_idx);
         }
       }
     }

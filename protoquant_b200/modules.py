@@ -10,6 +10,7 @@ from typing import Optional
 import torch
 from torch import nn
 
+from . import _lib
 from . import functional as F
 
 
@@ -53,7 +54,29 @@ class DynamicQuantLinear(nn.Module):
         return m
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return F.qlinear(x, self.qweight, self.weight_scale, self.bias, self.out_dtype or x.dtype, self.spec)
+        # Lean path: one C-ABI call (pq_qlinear = act-quant launch + GEMM launch), three allocations.
+        K, N = self.in_features, self.out_features
+        if (not x.is_cuda) or x.dtype not in F._DT or x.shape[-1] != K:
+            return F.qlinear(x, self.qweight, self.weight_scale, self.bias, self.out_dtype or x.dtype, self.spec)
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        out_dtype = self.out_dtype or x.dtype
+        if out_dtype not in F._DT:
+            raise TypeError(f"unsupported output dtype {out_dtype}")
+        wq = self.qweight_storage
+        y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        if M:
+            xq = torch.empty((M, wq.shape[1]), dtype=torch.int8, device=x.device)
+            sx = torch.empty((M,), dtype=torch.float32, device=x.device)
+            bias = self.bias
+            rc = _lib.lib().pq_qlinear(x2.data_ptr(), F._DT[x2.dtype], x2.stride(0), wq.data_ptr(), wq.stride(0),
+                                       self.weight_scale.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       y.data_ptr(), F._DT[out_dtype], N, xq.data_ptr(), sx.data_ptr(), M, N, K,
+                                       F._specp(self.spec), F._stream())
+            _lib.check(rc, "pq_qlinear")
+        return y.reshape(*x.shape[:-1], N)
 
     def dequantized_weight(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         return F.dequantize(self.qweight, self.weight_scale, axis=0, out_dtype=dtype)

@@ -92,3 +92,29 @@ def test_argument_validation_happens_before_device_checks_where_possible():
     assert b"y_dtype" in lib.pq_last_error()
     rc = lib.pq_dequant(p, 16, p, 2, p, 0, 16, 1, 16, None)
     assert rc == 1 and b"axis" in lib.pq_last_error()
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C (no C++isms, no torch types)."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(HEADER).read()
+    assert "at::" not in src and "std::" not in src
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` is the CPU arm the driver runs beside ours: one JSON line, oracle path."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "TOPS" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0

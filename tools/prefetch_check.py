@@ -18,7 +18,7 @@ def step(gemm_only=False):
         if not gemm_only:
             F.quantize_act(acts[src], out=ws[src])
         F.qgemm(ws[src][0], ws[src][1], m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
-for pf in (0, 1, 0, 1):
+for pf in (0, 2, 0, 2, 1):
     pq.lib().pq_debug_set_prefetch(pf)
     for gemm_only in (False, True):
         step(gemm_only); torch.cuda.synchronize()
