@@ -111,6 +111,19 @@ int pq_qlinear(const void* x, int x_dtype, int64_t ldx,
                const pq_quant_spec* spec, void* stream) {
   if (M == 0) return PQ_OK;
   if (!xq_ws || !sx_ws) PQ_FAIL(PQ_ERR_ARG, "pq_qlinear: null workspace");
+  if (M <= 32 && x && Wq && s_w && y && N > 0 && K > 0 && ldx >= K && ldy >= N &&
+      (y_dtype == PQ_BF16 || y_dtype == PQ_F16 || y_dtype == PQ_F32)) {
+    // decode batch: one fused launch (act-quant inside the weight-streaming GEMM) when eligible
+    int num_sms = 0;
+    int rc0 = check_device(&num_sms);
+    if (rc0) return rc0;
+    const pq_quant_spec sp = resolve_spec(spec);
+    if (sp.scale_mode >= PQ_DIV && sp.scale_mode <= PQ_INV_SCALE) {
+      rc0 = launch_qlinear_smallm_fused(x, x_dtype, ldx, Wq, ldb, s_w, bias, y, y_dtype, ldy, M, N, K, sp, num_sms,
+                                        (cudaStream_t)stream);
+      if (rc0 != 1) return rc0;
+    }
+  }
   const int64_t ldq = (K + 15) / 16 * 16;
   int rc = pq_act_quant(x, x_dtype, M, K, ldx, xq_ws, ldq, sx_ws, 0, spec, stream);
   if (rc) return rc;

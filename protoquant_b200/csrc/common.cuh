@@ -62,4 +62,10 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  void* const* outs, int n_out, int out_dtype, int64_t ldo,
                  int64_t M, int64_t N, int64_t K, cudaStream_t stream);
 
+int launch_qlinear_smallm_fused(const void* x, int x_dtype, int64_t ldx,
+                                const int8_t* b, int64_t ldb, const float* s_w, const float* bias,
+                                void* out, int out_dtype, int64_t ldo,
+                                int64_t M, int64_t N, int64_t K, const pq_quant_spec& spec,
+                                int num_sms, cudaStream_t stream);
+
 }  // namespace pq

@@ -2,6 +2,7 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld), clusters.
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
 #include <cuda.h>
 
 namespace pq {
@@ -51,6 +52,33 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
       : "memory");
+}
+// cluster-scope release arrive on a peer CTA's barrier / acquire wait: used when generic-proxy data
+// written into a peer's shared memory must be visible to the waiter
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void st_dsmem_u32(uint32_t local_addr, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(local_addr), "r"(cta), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
