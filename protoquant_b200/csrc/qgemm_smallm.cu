@@ -17,7 +17,7 @@
 #include "quant_math.cuh"
 
 namespace pq {
-int g_fused_decode = 1;   // pq_debug_set_fused_decode
+int g_fused_decode = 0;   // pq_debug_set_fused_decode; OFF: measured slower than quant kernel + PDL (profiles/README_r1.md)
 namespace {
 
 using namespace ptx;
@@ -256,6 +256,10 @@ qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
 //      tcgen05.mma expects for its N operand (what TMA would have produced);
 //   meanwhile warp 0 is already streaming the weights -- they do not depend on x.
 // One launch instead of two, and xq / s_x never touch global memory.
+// STATUS: bit-exact and tested, but OFF by default -- on B200 it measured 13.5 us vs 9.6 us for the
+// two-kernel path at 16 x 4096 x 4096: every channel-tile cluster re-quantises x, and that puts two
+// dependent L2 round trips plus a cluster barrier on each CTA's critical path, whereas the separate
+// 1.6 us quantizer kernel overlaps the GEMM's weight prefetch through PDL.
 struct FusedArgs {
   int M, N, K;
   int num_kb, splits;
@@ -331,7 +335,6 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_x, QTHREADS);
-    mbar_init(bar_amax, (uint32_t)(S * g.M));
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -344,8 +347,11 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
+  // The row-amax exchange uses one split-phase cluster barrier: warps that have nothing to publish
+  // arrive right away and only wait for it once their own work is done.
   if (warp == 0) {
     // ---- weight producer: independent of x, starts before the PDL wait ----
+    if (S > 1) cluster_arrive();
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -356,7 +362,9 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (S > 1) cluster_wait();
   } else if (warp == 1) {
+    if (S > 1) { cluster_arrive(); cluster_wait(); }
     if (lane == 0 && kb_end > kb_begin) {
       mbar_wait(bar_x, 0);                               // quantised slice is in shared memory
       tc_fence_after();
@@ -385,46 +393,21 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
     if (k_hi > g.K) k_hi = g.K;
     const int vpr = (k_hi > k_lo) ? (k_hi - k_lo) / EPV : 0;    // 16-byte vectors per row in the slice
     const int nv = g.M * vpr;
-    // A. row |.|-max of the slice
-    for (int v = qt; v < nv; v += QTHREADS) {
+    constexpr int VB = 8;                                       // independent 16-byte loads in flight per thread
+    const bool resident = nv <= QTHREADS * VB;                  // the whole slice fits in registers: read x once
+    uint4 keep[VB];
+    auto load_vec = [&](int v) -> uint4 {
       const int r = v / vpr, cv = v - r * vpr;
-      const uint4 raw = *reinterpret_cast<const uint4*>(x + (long long)r * g.ldx + k_lo + cv * EPV);
+      return *reinterpret_cast<const uint4*>(x + (long long)r * g.ldx + k_lo + cv * EPV);
+    };
+    auto vec_amax = [&](const uint4& raw) -> uint32_t {
       float a;
       if (sizeof(T) == 2) a = u16_mag_to_float<T>(absmax_u16x2(raw, 0u));
       else a = vec_absmax<float>(raw, 0.f);
-      atomicMax(amax_loc + r, __float_as_uint(a));         // non-negative floats order like their bits
-    }
-    named_bar_sync(1, QTHREADS);
-    if (qt < g.M) {
-      const uint32_t mine = amax_loc[qt];
-      if (S > 1) {
-        const uint32_t slot = smem_base + L::OFF_AMAX_ALL + (split * MP + (uint32_t)qt) * 4u;
-        for (int p = 0; p < S; ++p) {
-          st_dsmem_u32(slot, (uint32_t)p, mine);
-          mbar_arrive_remote_release(bar_amax, (uint32_t)p);
-        }
-      } else {
-        amax_all[qt] = mine;
-      }
-    }
-    if (S > 1) {
-      uint32_t polls = 0;
-      while (!mbar_try_wait_acq_cluster(bar_amax, 0)) {
-        if (++polls > 200000000u) { printf("pq: fused decode amax exchange timed out\n"); __trap(); }
-      }
-    } else {
-      named_bar_sync(1, QTHREADS);
-    }
-    if (qt < g.M) {
-      uint32_t m = 0;
-      for (int p = 0; p < S; ++p) m = max(m, amax_all[p * MP + qt]);
-      rowq[qt] = make_rowq(__uint_as_float(m), g.scale_mode, g.eps);
-    }
-    named_bar_sync(1, QTHREADS);
-    // B. quantise into the swizzled K-major operand layout
-    for (int v = qt; v < nv; v += QTHREADS) {
+      return __float_as_uint(a);                                // non-negative floats order like their bits
+    };
+    auto quant_store = [&](int v, const uint4& raw) {
       const int r = v / vpr, cv = v - r * vpr;
-      const uint4 raw = *reinterpret_cast<const uint4*>(x + (long long)r * g.ldx + k_lo + cv * EPV);
       const RowQ rq = rowq[r];
       float f[EPV];
       unpack<T>(raw, f);
@@ -444,6 +427,67 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
         *reinterpret_cast<uint2*>(dst) = o;
       } else {
         *reinterpret_cast<uint32_t*>(dst) = pack4(f[0], f[1], f[2], f[3]);
+      }
+    };
+    // A. row |.|-max of the slice (all loads of a batch are issued before any is used)
+    for (int base = 0; base < nv; base += QTHREADS * VB) {
+      uint4 raw[VB];
+#pragma unroll
+      for (int i = 0; i < VB; ++i) {
+        const int v = base + qt + i * QTHREADS;
+        raw[i] = make_uint4(0, 0, 0, 0);
+        if (v < nv) raw[i] = load_vec(v);
+      }
+#pragma unroll
+      for (int i = 0; i < VB; ++i) {
+        const int v = base + qt + i * QTHREADS;
+        if (v < nv) atomicMax(amax_loc + v / vpr, vec_amax(raw[i]));
+        keep[i] = raw[i];
+      }
+    }
+    named_bar_sync(1, QTHREADS);
+    if (qt < g.M) {
+      const uint32_t mine = amax_loc[qt];
+      if (S > 1) {
+        const uint32_t slot = smem_base + L::OFF_AMAX_ALL + (split * MP + (uint32_t)qt) * 4u;
+        for (int p = 0; p < S; ++p) st_dsmem_u32(slot, (uint32_t)p, mine);
+      } else {
+        amax_all[qt] = mine;
+      }
+    }
+    if (S > 1) {
+      cluster_arrive();      // release: the remote stores above are visible to every CTA after the wait
+      cluster_wait();
+    } else {
+      named_bar_sync(1, QTHREADS);
+    }
+    if (qt < g.M) {
+      uint32_t m = 0;
+      for (int p = 0; p < S; ++p) m = max(m, amax_all[p * MP + qt]);
+      rowq[qt] = make_rowq(__uint_as_float(m), g.scale_mode, g.eps);
+    }
+    named_bar_sync(1, QTHREADS);
+    // B. quantise into the swizzled K-major operand layout
+    if (resident) {
+#pragma unroll
+      for (int i = 0; i < VB; ++i) {
+        const int v = qt + i * QTHREADS;
+        if (v < nv) quant_store(v, keep[i]);
+      }
+    } else {
+      for (int base = 0; base < nv; base += QTHREADS * VB) {
+        uint4 raw[VB];
+#pragma unroll
+        for (int i = 0; i < VB; ++i) {
+          const int v = base + qt + i * QTHREADS;
+          raw[i] = make_uint4(0, 0, 0, 0);
+          if (v < nv) raw[i] = load_vec(v);
+        }
+#pragma unroll
+        for (int i = 0; i < VB; ++i) {
+          const int v = base + qt + i * QTHREADS;
+          if (v < nv) quant_store(v, raw[i]);
+        }
       }
     }
     fence_proxy_async_smem();                        // generic-proxy writes -> visible to tcgen05.mma

@@ -33,11 +33,7 @@ def test_dynamic_quant_linear_matches_oracle(dtype, name, features, tokens):
     m = pq.DynamicQuantLinear.from_float(lin.cuda())
     before = pq.launch_count()
     y = m(x.cuda())
-    M = 1
-    for t in tokens:
-        M *= t
-    fused_decode = M <= 32 and fin % 16 == 0        # decode batches: act-quant runs inside the GEMM kernel
-    assert pq.launch_count() - before == (1 if fused_decode else 2)   # nothing else is launched
+    assert pq.launch_count() - before == 2          # act-quant + GEMM, nothing else is launched
     assert y.shape == (*tokens, fout) and y.dtype == dtype
     lin = lin.cpu()
     wq, sw = O.quantize_weight(lin.weight.detach())
@@ -118,8 +114,8 @@ def test_sharded_module_nccl_bit_identical():
 @pytest.mark.parametrize("shape", [(1, 4096, 4096), (16, 4096, 4096), (7, 11008, 4096), (16, 4096, 11008), (32, 4096, 4096),
                                    (17, 768, 3072), (9, 3072, 768), (16, 136, 4096), (5, 264, 144), (16, 28672, 1024)])
 def test_fused_decode_linear_bit_exact(dtype, name, shape):
-    """activation quantisation fused into the small-M GEMM (one launch).  Must equal the
-    two-kernel path and the oracle bit for bit, for every scale-arithmetic knob."""
+    """activation quantisation fused into the small-M GEMM (one launch; experimental, off by
+    default).  Must equal the two-kernel path and the oracle bit for bit, for every scale-arithmetic knob."""
     M, N, K = shape
     g = torch.Generator().manual_seed(61)
     x = torch.randn(M, K, generator=g)
@@ -146,6 +142,6 @@ def test_fused_decode_linear_bit_exact(dtype, name, shape):
             outs.append(lin(x.cuda()))
             n = pq.launch_count() - before
             assert n == 2 if fused == 0 else n in (1, 2)
-        pq.lib().pq_debug_set_fused_decode(1)
+        pq.lib().pq_debug_set_fused_decode(0)      # default: off (measured slower, see profiles/README_r1.md)
         assert torch.equal(_bits(outs[0].cpu()), _bits(want))
         assert torch.equal(_bits(outs[1].cpu()), _bits(want))
