@@ -815,6 +815,30 @@ extern "C" void pq_debug_set_gemm_config(int cfg) { pq::g_force_cfg = cfg; }
 // -1 = heuristic, 0 = never use stream-K, 1 = use stream-K whenever it is legal
 extern "C" void pq_debug_set_streamk(int mode) { pq::g_sk_mode = mode; }
 extern "C" void pq_debug_set_staged(int on) { pq::g_force_staged = on; }
+// How many clusters of `cluster_size` CTAs of the main GEMM kernel fit on the device at once
+// (cudaOccupancyMaxActiveClusters); used to judge whether 4-CTA TMA multicast could pay.
+extern "C" int pq_debug_max_active_clusters(int cluster_size) {
+  using namespace pq;
+  using L = SmemLayout<2, 256, 6, false>;
+  auto kern = qgemm_kernel<2, 256, 6, __nv_bfloat16, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) return -1;
+  if (cluster_size > 8)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 * 4 / cluster_size * cluster_size, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = cluster_size;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return -2; }
+  return n;
+}
 extern "C" void pq_debug_set_prefetch(int on) { pq::g_prefetch_b = on; }
 // device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
 extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline = dev_buf; }
