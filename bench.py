@@ -563,9 +563,9 @@ def sharded_leg(pq, torch, dist, dev, rank, world):
 
 
 def main():
-    # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the one JSON line: NCCL prints its version banner (NCCL_DEBUG >= VERSION) to stdout
+    # unless it is given a debug file
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
