@@ -744,11 +744,24 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
   }
   int cfg = g_force_cfg;
   if (cfg < 0) {
-    const long long t256 = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
-    if (g.M > 128 && t256 * 2 >= num_sms) cfg = 1;
-    else if (g.M > 128) cfg = 4;
-    else if (g.N >= 1024) cfg = 0;   // small M: wide 1-CTA tiles, K split across SMs by stream-K
-    else cfg = 3;
+    // Measured on B200 (tools/sweep_mid.sh, profiles/README_r1.md):
+    //  * if some 1-CTA tile shape covers the problem in ONE wave, the shape with the most tiles wins
+    //    (M=256 x 4096^2: 128x64 tiles 10.0 us vs 256x256 pairs 16.9 us; M=512: 128x128 12.0 vs 17.1);
+    //  * otherwise 128x256 (1-CTA) vs 256x256 (CTA pair): the pair has the better steady state (fewer
+    //    operand bytes per MMA) but ~1 us more fixed cost, so it needs enough K blocks per worker.
+    const long long m128 = (g.M + 127) / 128;
+    const long long t0 = m128 * ((g.N + 255) / 256), t2 = m128 * ((g.N + 127) / 128), t3 = m128 * ((g.N + 63) / 64);
+    if (t3 <= num_sms) cfg = 3;
+    else if (t2 <= num_sms) cfg = 2;
+    else if (t0 <= num_sms) cfg = 0;
+    else {
+      const long long t1 = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
+      const long long pairs = num_sms / 2;
+      const long long w0 = (t0 + num_sms - 1) / num_sms, w1 = (t1 + pairs - 1) / pairs;
+      const double eff0 = (double)t0 / (double)(w0 * num_sms), eff1 = (double)t1 / (double)(w1 * pairs);
+      const long long kb = (g.K + BLOCK_K - 1) / BLOCK_K;
+      cfg = (eff1 + 0.03 >= eff0 && w1 * kb > 80) ? 1 : 0;
+    }
   }
   switch (cfg) {
     case 0: return launch_cfg<1, 256, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
