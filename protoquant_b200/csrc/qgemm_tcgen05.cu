@@ -22,6 +22,7 @@
 // 256 x BLOCK_N tile, each CTA stages its own 128 rows of A and its half of B, the even
 // CTA issues the MMAs for both and multicasts the commits.
 #include "gemm_common.cuh"
+#include <string.h>
 
 namespace pq {
 int launch_qgemm_smallm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
@@ -54,6 +55,7 @@ struct GemmArgs {
   int* sk_flags;      // [workers*CG][2] ticket / done counters (self-cleaning, zero between launches)
   unsigned long long* tl;   // debug timeline (32 x u64 per CTA) or null
   int prefetch_b;           // 1 = warp 3 prefetches this CTA's weight boxes into L2 ahead of the ring
+  int tma_store;            // staged epilogue hands its tiles to TMA bulk stores (single destination)
 };
 
 template <int CG, int BN, int STAGES, bool STAGED = false>
@@ -164,7 +166,8 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
-             const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+             const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ CUtensorMap tmap_y, const GemmArgs g) {
   using L = SmemLayout<CG, BN, STAGES, STAGED>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
   static_assert(!(STAGED && RAW), "staged epilogue is for typed outputs only");
@@ -201,6 +204,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     PQ_TL(0);
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (STAGED && g.tma_store) prefetch_tmap(&tmap_y);
   }
   if (warp == 1 && lane == 0) {
     *prod_count = 0;
@@ -430,19 +434,29 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       __syncwarp();
       if constexpr (STAGED) {
+        // Staging tile of one column half and one pass: two sub-boxes of [128 rows x 128 B], each
+        // laid out exactly like a 128B-swizzled TMA box (16-byte unit u of row r sits at u ^ (r & 7)).
         using OT = typename std::conditional<RAW, float, OutT>::type;
-        constexpr int ROWB = 256;                                  // staged bytes per row
+        constexpr int ROWB = 256;                                  // staged bytes per row and pass
         constexpr int ESZ = (int)sizeof(OT);
         constexpr int COLS_PASS = ROWB / ESZ;                      // 128 (16-bit) or 64 (fp32)
         constexpr int CH_PASS = COLS_PASS / 32;
         constexpr int PASSES = (BN / 2) / COLS_PASS;
         constexpr int UPC = OutPack<OT>::WORDS / 4;                // 16-byte units per 32-column chunk
         constexpr int EPU = 16 / ESZ;                              // elements per 16-byte unit
+        constexpr int SUB = 16384;                                 // bytes per sub-box
         uint8_t* stg = smem_gen + L::OFF_STAGE_OUT + half * 32768;
+        const uint32_t stg_u32 = smem_base + L::OFF_STAGE_OUT + half * 32768;
         const int gt = etid & 127;                                 // thread index inside this column half
         const int m0 = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+        const bool tma_out = g.tma_store != 0;
 #pragma unroll 1
         for (int pass = 0; pass < PASSES; ++pass) {
+          if (tma_out) {
+            // the bulk stores issued from this staging tile must have finished READING it
+            if (gt == 0) tma_store_wait_read<0>();
+            if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
+          }
 #pragma unroll 1
           for (int cc = 0; cc < CH_PASS; ++cc) {
             const int c = c_lo + pass * CH_PASS + cc;
@@ -471,43 +485,55 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             OutPack<OT>::pack(f, o);
 #pragma unroll
             for (int i = 0; i < UPC; ++i) {
-              const int u = cc * UPC + i;
-              *reinterpret_cast<uint4*>(stg + et * ROWB + ((u ^ (et & 7)) << 4)) =
+              const int u = cc * UPC + i;                          // unit inside the 256-byte pass row
+              *reinterpret_cast<uint4*>(stg + (u >> 3) * SUB + et * 128 + (((u & 7) ^ (et & 7)) << 4)) =
                   make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             }
           }
           if (pass == PASSES - 1) {
-            // accumulator fully read: give the TMEM buffer back before the (slow) copy-out
+            // accumulator fully read: give the TMEM buffer back before the copy-out
             tc_fence_before();
             if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
             else mbar_arrive_remote(bar_tempty + as * 8, 0);
           }
-          if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
-          // copy-out: a warp instruction moves two whole 256-byte row segments per destination
           const int colp = col0 + half * (BN / 2) + pass * COLS_PASS;
+          if (tma_out) {
+            // one thread hands both sub-boxes to the TMA store engine: full-line writes, rows >= M and
+            // columns >= N are clipped by the tensor map
+            fence_proxy_async_smem();
+            if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
+            if (gt == 0 && m0 < g.M) {
+              if (colp < g.N) tma_store_2d(&tmap_y, stg_u32, colp, m0);
+              if (colp + 128 / ESZ < g.N) tma_store_2d(&tmap_y, stg_u32 + SUB, colp + 128 / ESZ, m0);
+              tma_store_commit();
+            }
+          } else {
+            if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
+            // LSU copy-out: a warp instruction moves two whole 256-byte row segments per destination
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int idx = i * 128 + gt;
-            const int rr = idx >> 4, u = idx & 15;
-            const int grow = m0 + rr;
-            const int gcol = colp + u * EPU;
-            if (grow < g.M && gcol < g.N) {
-              const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * ROWB + ((u ^ (rr & 7)) << 4));
-              if (g.vec_ok && gcol + EPU <= g.N) {
-                for (int d = 0; d < g.n_out; ++d)
-                  *reinterpret_cast<uint4*>(reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol) = v;
-              } else {
-                const OT* ev = reinterpret_cast<const OT*>(&v);
-                for (int d = 0; d < g.n_out; ++d) {
-                  OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol;
+            for (int i = 0; i < 16; ++i) {
+              const int idx = i * 128 + gt;
+              const int rr = idx >> 4, u = idx & 15;
+              const int grow = m0 + rr;
+              const int gcol = colp + u * EPU;
+              if (grow < g.M && gcol < g.N) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + (u >> 3) * SUB + rr * 128 + (((u & 7) ^ (rr & 7)) << 4));
+                if (g.vec_ok && gcol + EPU <= g.N) {
+                  for (int d = 0; d < g.n_out; ++d)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol) = v;
+                } else {
+                  const OT* ev = reinterpret_cast<const OT*>(&v);
+                  for (int d = 0; d < g.n_out; ++d) {
+                    OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol;
 #pragma unroll
-                  for (int e = 0; e < EPU; ++e)
-                    if (gcol + e < g.N) dst[e] = ev[e];
+                    for (int e = 0; e < EPU; ++e)
+                      if (gcol + e < g.N) dst[e] = ev[e];
+                  }
                 }
               }
             }
+            if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
           }
-          if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
         }
         continue;
       }
@@ -588,6 +614,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
       else mbar_arrive_remote(bar_tempty + as * 8, 0);
     }
+    if constexpr (STAGED) {
+      if (g.tma_store && (etid & 127) == 0) tma_store_wait<0>();   // staging smem must outlive the bulk stores
+    }
   }
 
   __syncwarp();
@@ -614,6 +643,7 @@ struct SkPool {
 };
 SkPool g_sk_pool[64];
 unsigned long long* g_timeline = nullptr;
+int g_tma_store = 1;     // staged epilogue uses TMA bulk stores when it can (pq_debug_set_tma_store)
 int g_sk_mode = 0;   // 0 never (default until the fix-up path is cheap enough), 1 whenever legal, -1 heuristic
 
 bool sk_alloc_slot(SkPool& pool, int num_sms) {
@@ -672,6 +702,23 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   rc = make_tmap(&tb, b, g.N, g.K, ldb, L::B_ROWS);
   if (rc) return rc;
 
+  CUtensorMap ty;
+  memset(&ty, 0, sizeof(ty));
+  g.tma_store = 0;
+  if (STAGED && g.n_out == 1 && g.vec_ok && g_tma_store) {
+    // output as [M rows] x [N elements], boxes of 128 bytes x 128 rows, same 128B swizzle as the staging tile
+    constexpr int esz = (int)sizeof(OutT);
+    auto fn = get_encode_fn();
+    if (!fn) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+    cuuint64_t strides[1] = {(cuuint64_t)(g.ldo * esz)};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)BLOCK_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&ty, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, g.out[0], dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) g.tma_store = 1;
+  }
   auto kern = qgemm_kernel<CG, BN, STAGES, OutT, STAGED>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -720,7 +767,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ty, g));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;
 }
@@ -860,5 +907,6 @@ extern "C" int pq_debug_max_active_clusters(int cluster_size) {
   return n;
 }
 extern "C" void pq_debug_set_prefetch(int on) { pq::g_prefetch_b = on; }
+extern "C" void pq_debug_set_tma_store(int on) { pq::g_tma_store = on; }
 // device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
 extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline = dev_buf; }
