@@ -800,8 +800,13 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
     const long long t0 = m128 * ((g.N + 255) / 256), t2 = m128 * ((g.N + 127) / 128), t3 = m128 * ((g.N + 63) / 64);
     if (t3 <= num_sms) cfg = 3;
     else if (t2 <= num_sms) cfg = 2;
-    else if (t0 <= num_sms) cfg = 0;
-    else {
+    else if (t0 <= num_sms) {
+      cfg = 0;
+      if constexpr (!std::is_same<OutT, int32_t>::value) {   // one short-K wave: the epilogue is the kernel
+        if ((g.K + BLOCK_K - 1) / BLOCK_K <= 16 && g.vec_ok && g_force_cfg < 0)
+          return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+      }
+    } else {
       const long long t1 = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
       const long long pairs = num_sms / 2;
       const long long w0 = (t0 + num_sms - 1) / num_sms, w1 = (t1 + pairs - 1) / pairs;
