@@ -213,9 +213,10 @@ def run_ours(args):
     outs = {name: torch.empty(M_TOKENS, n, dtype=torch.bfloat16, device=dev) for name, k, n, _ in LINEARS}
 
     def linear_fwd(name, src):
+        # the module's own forward path (one pq_qlinear call = act-quant launch + GEMM launch) on
+        # preallocated buffers, so that the step can be captured into a CUDA graph
         m = mods[name]
-        xq, sx = F.quantize_act(acts[src], out=xq_ws[src])
-        F.qgemm(xq, sx, m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
+        F.qlinear_into(acts[src], m.qweight_storage, m.in_features, m.weight_scale, m.bias, outs[name], *xq_ws[src])
 
     def step():
         for name, k, n, src in LINEARS:

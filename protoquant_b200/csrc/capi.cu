@@ -125,7 +125,13 @@ int pq_qlinear(const void* x, int x_dtype, int64_t ldx,
     }
   }
   const int64_t ldq = (K + 15) / 16 * 16;
-  int rc = pq_act_quant(x, x_dtype, M, K, ldx, xq_ws, ldq, sx_ws, 0, spec, stream);
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  // M > 64: the tcgen05 GEMM re-reads each weight tile from L2 once per 256 tokens; have the quantizer
+  // pull the (DRAM-cold) weights into L2 meanwhile.  Capped well below the 126 MB L2.
+  const long long w_bytes = (M > 64 && Wq && N > 0) ? (long long)N * ldb : 0;
+  rc = launch_rowwise_quant(x, x_dtype, M, K, ldx, xq_ws, ldq, sx_ws, 0, resolve_spec(spec), (cudaStream_t)stream,
+                            Wq, w_bytes < (64LL << 20) ? w_bytes : (64LL << 20));
   if (rc) return rc;
   return pq_qgemm(xq_ws, ldq, Wq, ldb, sx_ws, s_w, bias, y, y_dtype, ldy, M, N, K, stream);
 }

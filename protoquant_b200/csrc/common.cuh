@@ -55,7 +55,8 @@ inline int dtype_size(int dt) {
 // ---- internal launchers shared between translation units ------------------------
 int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
                          int8_t* xq, int64_t ldq, float* s, int transpose,
-                         const pq_quant_spec& spec, cudaStream_t stream);
+                         const pq_quant_spec& spec, cudaStream_t stream,
+                         const void* prefetch = nullptr, long long prefetch_bytes = 0);
 
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,

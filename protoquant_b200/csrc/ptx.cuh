@@ -140,6 +140,20 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(m), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same, multicast: the box lands at the same shared-memory offset in every CTA of `mask` (cluster
+// ranks), and each destination's bytes are credited to the barrier at this offset in the leader
+// (even) CTA of that destination's pair.
+__device__ __forceinline__ void tma_load_2d_2sm_mcast(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                      int32_t c0, int32_t c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(m), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// Pull `bytes` (multiple of 16) starting at the 16-byte aligned global address `p` into L2.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // Pull a tensor-map box into L2 only (no shared-memory destination, no barrier).
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1)
@@ -217,8 +231,9 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 }
 // mbarrier arrive when all previously issued tcgen05 ops of this thread have completed.
 // CG == 2: the arrive is multicast to the barrier at this offset in both CTAs of the pair.
+// `mask` = cluster ranks whose barrier receives the arrive (default: the two CTAs of a 2-CTA cluster).
 template <int CG>
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
+__device__ __forceinline__ void tc_commit(uint32_t bar, uint16_t mask = 3) {
   if (CG == 1)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
@@ -226,7 +241,7 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
             "r"(bar),
-        "h"((uint16_t)3)
+        "h"(mask)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {

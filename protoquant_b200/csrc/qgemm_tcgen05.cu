@@ -56,9 +56,13 @@ struct GemmArgs {
   unsigned long long* tl;   // debug timeline (32 x u64 per CTA) or null
   int prefetch_b;           // 1 = warp 3 prefetches this CTA's weight boxes into L2 ahead of the ring
   int tma_store;            // staged epilogue hands its tiles to TMA bulk stores (single destination)
+  int dbg;                  // profiling only (pq_debug_set_epilogue): bit 0 = the epilogue skips its global stores
 };
 
-template <int CG, int BN, int STAGES, bool STAGED = false>
+// WS_BYTES: per-warp TMA-store staging of the direct epilogue (16-bit outputs): every epilogue warp owns
+// WS_NBUF boxes of [32 rows x 64 B]; 0 = no staging (fp32 / int32 outputs keep per-lane global stores).
+constexpr int NUM_BARS_C(int stages) { return 2 * stages + 4; }
+template <int CG, int BN, int STAGES, bool STAGED = false, int OUT_BYTES = 4>
 struct SmemLayout {
   static constexpr int A_STAGE = BLOCK_M * BLOCK_K;
   static constexpr int B_ROWS = BN / CG;
@@ -68,9 +72,16 @@ struct SmemLayout {
   static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
   static constexpr int STAGE_OUT = STAGED ? 2 * 32768 : 0;  // per column-half [128 rows][256 B] output staging
   static constexpr int OFF_STAGE_OUT = OFF_B + STAGES * B_STAGE;
-  static constexpr int OFF_SW = OFF_STAGE_OUT + STAGE_OUT;  // [2][BN] fp32
-  static constexpr int OFF_BIAS = OFF_SW + 2 * BN * 4;      // [2][BN] fp32
-  static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;     // full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int BNP = (BN + 31) / 32 * 32;           // columns rounded up to whole 32-column chunks
+  static constexpr int WS_BOX = 32 * 64;                    // one warp's box: 32 rows x 32 sixteen-bit columns
+  static constexpr int WS_FIXED = STAGES * (A_STAGE + B_STAGE) + 4 * BNP * 4 + NUM_BARS_C(STAGES) * 8 + 16 + 1024;
+  static constexpr int WS_NBUF = (OUT_BYTES != 2 || STAGED) ? 0 : (WS_FIXED + 2 * 8 * WS_BOX <= 227 * 1024) ? 2
+                                 : (WS_FIXED + 8 * WS_BOX <= 227 * 1024) ? 1 : 0;
+  static constexpr int WS_BYTES = WS_NBUF * 8 * WS_BOX;
+  static constexpr int OFF_WS = OFF_STAGE_OUT + STAGE_OUT;  // 1024-aligned: every term before it is
+  static constexpr int OFF_SW = OFF_WS + WS_BYTES;          // [2][BNP] fp32
+  static constexpr int OFF_BIAS = OFF_SW + 2 * BNP * 4;     // [2][BNP] fp32
+  static constexpr int OFF_BAR = OFF_BIAS + 2 * BNP * 4;    // full[S], empty[S], tfull[2], tempty[2]
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int OFF_MISC = OFF_TMEM_PTR + 8;           // stream-K ticket broadcast
@@ -163,20 +174,29 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // STAGED = true: the epilogue goes through shared memory so that every global store
 // instruction writes whole 256-byte row segments (needed for NVLink peer / multicast
 // destinations, where 16-byte scattered writes waste most of the link).
-template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false>
+// MC == 2: two CTA pairs form a 4-CTA cluster working on a 512 x BN super-tile (pair p takes rows
+// p*256..): both pairs need the same weight tile, so each CTA fetches only half of its B slice and
+// TMA-multicasts it to the CTA with the same rank in the other pair.  L2 -> SM operand bytes per
+// MMA drop by 25 % (the main loop is bound by L2 slice throughput, profiles/README_r1.md).
+template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false, int MC = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
              const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_y, const GemmArgs g) {
-  using L = SmemLayout<CG, BN, STAGES, STAGED>;
+  using L = SmemLayout<CG, BN, STAGES, STAGED, (int)sizeof(OutT)>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
   static_assert(!(STAGED && RAW), "staged epilogue is for typed outputs only");
   static_assert(!STAGED || BN == 256, "staged epilogue assumes 128-column halves");
+  static_assert(MC == 1 || (MC == 2 && CG == 2 && (BN / 4) % 8 == 0), "multicast clusters are pairs of CTA pairs");
+  constexpr int SUPER_M = BLOCK_M * CG * MC;   // rows of one scheduled tile (all CTAs of the cluster)
   constexpr int UMMA_M = BLOCK_M * CG;
   constexpr int UMMA_N = BN;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                 : (2 * BN <= 256) ? 256 : 512;
-  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BLOCK_N must be a multiple of 64 in [64,256]");
+  // accumulator buffer stride in TMEM columns: BN rounded up to a power of two (so BN = 240 keeps the
+  // second buffer at column 256)
+  constexpr uint32_t TSTRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * TSTRIDE;
+  constexpr int BNP = L::BNP;
+  static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BLOCK_N must be a multiple of 16 in [64,256]");
   static_assert(UMMA_N % 16 == 0, "invalid UMMA N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -185,8 +205,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cl_rank = (CG * MC > 1) ? cluster_ctarank() : 0u;   // rank in the cluster
+  const uint32_t cta_rank = cl_rank & (CG - 1);                      // rank inside the MMA pair
+  const uint32_t pair_id = cl_rank >> 1;                             // which pair of the cluster (MC == 2)
+  const uint32_t leader_rank = pair_id * 2;                          // cluster rank of this pair's MMA-issuing CTA
   const bool leader = (cta_rank == 0);
+  const int m_off = (int)pair_id * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;   // this CTA's rows inside the tile
+  const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
+  const uint16_t all_mask = (uint16_t)((1u << (CG * MC)) - 1u);
 
   const uint32_t bar_full = smem_base + L::OFF_BAR;
   const uint32_t bar_empty = bar_full + STAGES * 8;
@@ -204,13 +230,13 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     PQ_TL(0);
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    if (STAGED && g.tma_store) prefetch_tmap(&tmap_y);
+    if (g.tma_store) prefetch_tmap(&tmap_y);
   }
   if (warp == 1 && lane == 0) {
     *prod_count = 0;
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bar_full + i * 8, CG);   // one producer arrive per CTA of the pair (leader's copy is used)
-      mbar_init(bar_empty + i * 8, 1);   // one tcgen05.commit
+      mbar_init(bar_empty + i * 8, MC);  // one tcgen05.commit per pair that reads (or multicasts into) the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);                   // one tcgen05.commit
@@ -232,8 +258,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // prefetcher only touches the (static) weights, so it does not wait.
   if (!(warp == 3 && lane == 0)) griddep_wait();
 
-  const int num_clusters = gridDim.x / CG;
-  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / (CG * MC);
+  const int cluster_id = blockIdx.x / (CG * MC);
   Sched sched;
   sched.init(g, cluster_id, num_clusters);
   if (threadIdx.x == 0) PQ_TL(1);
@@ -246,7 +272,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       while (sched.next(tile, kb0, kb1)) {
         int m_blk, n_blk;
         tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
-        const int m_idx = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+        const int m_idx = m_blk * SUPER_M + m_off;
         const int n_idx = n_blk * BN + (int)cta_rank * L::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1);
@@ -259,9 +285,16 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tma_load_2d(sb, &tmap_b, fb, kb * BLOCK_K, n_idx);
           } else {
             tma_load_2d_2sm(sa, &tmap_a, fb, kb * BLOCK_K, m_idx);
-            tma_load_2d_2sm(sb, &tmap_b, fb, kb * BLOCK_K, n_idx);
+            if (MC == 1) {
+              tma_load_2d_2sm(sb, &tmap_b, fb, kb * BLOCK_K, n_idx);
+            } else {
+              // my half of this rank's B slice, delivered to both pairs
+              constexpr int HROWS = L::B_ROWS / 2;
+              tma_load_2d_2sm_mcast(sb + pair_id * (HROWS * BLOCK_K), &tmap_b, fb, kb * BLOCK_K,
+                                    n_idx + (int)pair_id * HROWS, (uint16_t)(5u << cta_rank));
+            }
             if (leader) mbar_arrive_expect_tx(fb, L::STAGE_BYTES * 2);
-            else mbar_arrive_remote(fb, 0);
+            else mbar_arrive_remote(fb, leader_rank);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           *prod_count = *prod_count + 1;
@@ -305,7 +338,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(bar_tempty + as * 8, aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * TSTRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
@@ -318,8 +351,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mma_i8<CG>(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
                        idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
-          tc_commit<CG>(bar_empty + stage * 8);
-          if (kb == kb1 - 1) tc_commit<CG>(bar_tfull + as * 8);
+          tc_commit<CG>(bar_empty + stage * 8, all_mask);
+          if (kb == kb1 - 1) tc_commit<CG>(bar_tfull + as * 8, pair_mask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -341,8 +374,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int half = (warp - EPI_WARP0) >> 2;    // which half of the tile's columns this warp handles
     const int et = ew * 32 + (int)lane;          // row inside the CTA's 128-row slab
     const int etid = (int)threadIdx.x - EPI_WARP0 * 32;   // 0..255
-    constexpr int CH = BN / 64;                  // 32-column chunks per warp
-    const int c_lo = half * CH, c_hi = c_lo + CH;
+    constexpr int NCH = BNP / 32;                // 32-column chunks per tile (the last may be half a chunk)
+    constexpr int CH = (NCH + 1) / 2;            // chunks of the left-half warps
+    const int c_lo = half * CH, c_hi = half ? NCH : CH;
     const bool has_bias = g.bias != nullptr;   // without bias there is no add at all (-0.0 stays -0.0)
     int iter = 0;
     int tile, kb0, kb1;
@@ -350,10 +384,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int m_blk, n_blk;
       tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
-      const int row = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M + et;
+      const int row = m_blk * SUPER_M + m_off + et;
       const int col0 = n_blk * BN;
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
-      constexpr long long SLOT = (long long)BN * BLOCK_M;   // int32 elements per CTA partial
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + as * TSTRIDE;
+      const int n_end = min(g.N, col0 + BN);     // first column past this tile
+      constexpr long long SLOT = (long long)BNP * BLOCK_M;   // int32 elements per CTA partial
       // ---- stream-K: a split tile is completed by whichever participant finishes last ----
       // Every participant takes a ticket once its own accumulator is complete.  All but the last
       // dump their raw int32 partial into their own workspace slot (plain coalesced stores) and
@@ -383,14 +418,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint32_t r[32];
           tmem_ld_32x32(taddr0 + c * 32, r);
           tmem_ld_wait();
-          if (row < g.M && col0 + c * 32 < g.N) {
+          if (row < g.M && col0 + c * 32 < n_end) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) __stcg(slot + (c * 32 + j) * BLOCK_M + et, (int)r[j]);
           }
         }
         tc_fence_before();
         if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
-        else mbar_arrive_remote(bar_tempty + as * 8, 0);
+        else mbar_arrive_remote(bar_tempty + as * 8, leader_rank);
         __threadfence();
         named_bar_sync(1, EPI_THREADS);
         if (etid == 0) atomicAdd(ctr + 1, 1);
@@ -420,9 +455,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       float sx = 0.f;
       if constexpr (!RAW) {
         // stage this tile's column scales / bias (double-buffered by accumulator stage)
-        float* sw = sw_smem + as * BN;
-        float* bs = bias_smem + as * BN;
-        for (int i = etid; i < BN; i += EPI_THREADS) {
+        float* sw = sw_smem + as * BNP;
+        float* bs = bias_smem + as * BNP;
+        for (int i = etid; i < BNP; i += EPI_THREADS) {
           const int c = col0 + i;
           sw[i] = (c < g.N) ? __ldg(g.s_w + c) : 0.f;
           bs[i] = (g.bias != nullptr && c < g.N) ? __ldg(g.bias + c) : 0.f;
@@ -433,6 +468,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(bar_tfull + as * 8, aphase);
       tc_fence_after();
       __syncwarp();
+      if (etid == 0 && iter < 5 && !split) PQ_TL(8 + iter * 4 + 0);
       if constexpr (STAGED) {
         // Staging tile of one column half and one pass: two sub-boxes of [128 rows x 128 B], each
         // laid out exactly like a 128B-swizzled TMA box (16-byte unit u of row r sits at u ^ (r & 7)).
@@ -448,7 +484,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint8_t* stg = smem_gen + L::OFF_STAGE_OUT + half * 32768;
         const uint32_t stg_u32 = smem_base + L::OFF_STAGE_OUT + half * 32768;
         const int gt = etid & 127;                                 // thread index inside this column half
-        const int m0 = m_blk * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+        const int m0 = m_blk * SUPER_M + m_off;
         const bool tma_out = g.tma_store != 0;
 #pragma unroll 1
         for (int pass = 0; pass < PASSES; ++pass) {
@@ -463,8 +499,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t r[32];
             tmem_ld_32x32(taddr0 + c * 32, r);
             tmem_ld_wait();
-            const float* sw = sw_smem + as * BN + c * 32;
-            const float* bs = bias_smem + as * BN + c * 32;
+            const float* sw = sw_smem + as * BNP + c * 32;
+            const float* bs = bias_smem + as * BNP + c * 32;
             float f[32];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -494,7 +530,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // accumulator fully read: give the TMEM buffer back before the copy-out
             tc_fence_before();
             if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
-            else mbar_arrive_remote(bar_tempty + as * 8, 0);
+            else mbar_arrive_remote(bar_tempty + as * 8, leader_rank);
           }
           const int colp = col0 + half * (BN / 2) + pass * COLS_PASS;
           if (tma_out) {
@@ -537,13 +573,88 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         continue;
       }
+      if constexpr (L::WS_NBUF > 0) {
+        if (g.tma_store) {
+          // ---- 16-bit outputs: per-warp TMA-store epilogue ----
+          // Every warp converts one 32-column chunk at a time into its own [32 rows x 64 B] box (laid out
+          // like a 64B-swizzled TMA box, conflict-free 16-byte shared stores) and hands it to the TMA
+          // store engine: full-sector writes and ~40x fewer LSU wavefronts than one-row-per-lane global
+          // stores, which were measured to slow the concurrent main loop (profiles/README_r1.md).  M and
+          // N tails are clipped by the tensor map; a tile whose width is not a multiple of 32 re-stores
+          // the overlap of its last two chunks (same values).
+          const int wslot = warp - EPI_WARP0;
+          const uint32_t ws_u32 = smem_base + L::OFF_WS + wslot * (L::WS_NBUF * L::WS_BOX);
+          uint8_t* ws_gen = smem_gen + L::OFF_WS + wslot * (L::WS_NBUF * L::WS_BOX);
+          const int row0 = m_blk * SUPER_M + m_off + ew * 32;
+          const float* swb = sw_smem + as * BNP;
+          const float* bsb = bias_smem + as * BNP;
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            const int ct = min(c * 32, BN - 32);   // tile-relative first column of this chunk
+            uint32_t r[32];
+            tmem_ld_32x32(taddr0 + ct, r);
+            tmem_ld_wait();
+            if (c == c_hi - 1) {                   // accumulator fully read by this thread
+              tc_fence_before();
+              if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
+              else mbar_arrive_remote(bar_tempty + as * 8, leader_rank);
+            }
+            if (role == 2 && row < g.M && col0 + ct < n_end) {
+              for (int q = fw; q <= lw; ++q) {
+                if (q == sched.worker) continue;
+                const int which = (sched.U * q / sched.workers > (long long)tile * sched.KB) ? 0 : 1;
+                const int32_t* ps = g.sk_ws + (((long long)q * 2 + which) * CG + cta_rank) * SLOT + ct * BLOCK_M + et;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] += (uint32_t)__ldcg(ps + j * BLOCK_M);
+              }
+            }
+            float f[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(swb + ct + 4 * j4);
+              const float4 b4 = *reinterpret_cast<const float4*>(bsb + ct + 4 * j4);
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+              const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v = __int2float_rn((int)r[4 * j4 + j]);
+                v = __fmul_rn(v, sx);
+                v = __fmul_rn(v, wv[j]);
+                if (has_bias) v = __fadd_rn(v, bv[j]);
+                f[4 * j4 + j] = v;
+              }
+            }
+            using OT = typename std::conditional<RAW, float, OutT>::type;
+            uint32_t o[OutPack<OT>::WORDS];
+            OutPack<OT>::pack(f, o);
+            const int buf = (L::WS_NBUF == 2) ? ((c - c_lo) & 1) : 0;
+            if (lane == 0) tma_store_wait_read<(L::WS_NBUF > 1) ? L::WS_NBUF - 1 : 0>();   // the box is free again
+            __syncwarp();
+            uint8_t* box = ws_gen + buf * L::WS_BOX + lane * 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(box + ((i ^ (((int)lane >> 1) & 3)) << 4)) =
+                  make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (row0 < g.M && col0 + ct < g.N && !(g.dbg & 1))
+                tma_store_2d(&tmap_y, ws_u32 + buf * L::WS_BOX, col0 + ct, row0);
+              tma_store_commit();
+            }
+          }
+          if (etid == 0 && iter < 5) PQ_TL(8 + iter * 4 + 3);
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr0 + c * 32, r);
         tmem_ld_wait();
         const int col = col0 + c * 32;
-        if (row < g.M && col < g.N) {
+        const int lim = (g.dbg & 1) ? 0 : n_end - col;   // valid columns of this chunk (>= 32: all of them)
+        if (row < g.M && lim > 0) {
           if (role == 2) {
             // fold in the other participants' partial sums (slot 0 = their first-tile tail,
             // slot 1 = their last-tile head)
@@ -558,20 +669,24 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if constexpr (RAW) {
             for (int d = 0; d < g.n_out; ++d) {
               int32_t* dst = reinterpret_cast<int32_t*>(g.out[d]) + (long long)row * g.ldo + col;
-              if (g.vec_ok && col + 32 <= g.N) {
+              if (g.vec_ok && lim >= 32) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<uint4*>(dst)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+              } else if (g.vec_ok && lim == 16) {   // half chunk at the end of a BN % 32 == 16 tile
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
                   reinterpret_cast<uint4*>(dst)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (col + j < g.N) dst[j] = (int32_t)r[j];
+                  if (j < lim) dst[j] = (int32_t)r[j];
               }
             }
           } else {
             using OT = typename std::conditional<RAW, float, OutT>::type;
-            const float* sw = sw_smem + as * BN + c * 32;
-            const float* bs = bias_smem + as * BN + c * 32;
+            const float* sw = sw_smem + as * BNP + c * 32;
+            const float* bs = bias_smem + as * BNP + c * 32;
             float f[32];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -588,21 +703,22 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 f[4 * j4 + j] = v;
               }
             }
-            if (g.vec_ok && col + 32 <= g.N) {
+            if (g.vec_ok && (lim >= 32 || lim == 16)) {
               uint32_t o[OutPack<OT>::WORDS];
               OutPack<OT>::pack(f, o);
               for (int d = 0; d < g.n_out; ++d) {
                 OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)row * g.ldo + col;
 #pragma unroll
                 for (int i = 0; i < OutPack<OT>::WORDS / 4; ++i)
-                  reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                  if (i < OutPack<OT>::WORDS / 8 || lim >= 32)   // lim == 16: first half of the chunk only
+                    reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
               }
             } else {
               for (int d = 0; d < g.n_out; ++d) {
                 OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)row * g.ldo + col;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (col + j < g.N) dst[j] = OutPack<OT>::one(f[j]);
+                  if (j < lim) dst[j] = OutPack<OT>::one(f[j]);
               }
             }
           }
@@ -612,10 +728,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // accumulator buffer fully read: hand it back to the MMA warp (leader CTA's barrier)
       tc_fence_before();
       if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
-      else mbar_arrive_remote(bar_tempty + as * 8, 0);
+      else mbar_arrive_remote(bar_tempty + as * 8, leader_rank);
     }
     if constexpr (STAGED) {
       if (g.tma_store && (etid & 127) == 0) tma_store_wait<0>();   // staging smem must outlive the bulk stores
+    } else if constexpr (L::WS_NBUF > 0) {
+      if (g.tma_store && lane == 0) tma_store_wait<0>();
     }
   }
 
@@ -688,18 +806,18 @@ SkSlot* sk_get_slot(int dev, int num_sms, cudaStream_t st) {
   return free_slot;
 }
 
-template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false>
+template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false, int MC = 1>
 int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g0,
                int num_sms, cudaStream_t st) {
-  using L = SmemLayout<CG, BN, STAGES, STAGED>;
+  using L = SmemLayout<CG, BN, STAGES, STAGED, (int)sizeof(OutT)>;
   GemmArgs g = g0;
-  g.num_m_blocks = (g.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+  g.num_m_blocks = (g.M + BLOCK_M * CG * MC - 1) / (BLOCK_M * CG * MC);
   g.num_n_blocks = (g.N + BN - 1) / BN;
   g.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, a, g.M, g.K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap(&tb, b, g.N, g.K, ldb, L::B_ROWS);
+  rc = make_tmap(&tb, b, g.N, g.K, ldb, L::B_ROWS / MC);
   if (rc) return rc;
 
   CUtensorMap ty;
@@ -718,18 +836,48 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) g.tma_store = 1;
+  } else if (L::WS_NBUF > 0 && g.n_out == 1 && g.vec_ok && g_tma_store) {
+    // per-warp epilogue boxes: [32 rows] x [32 sixteen-bit columns], 64B swizzle
+    auto fn = get_encode_fn();
+    if (!fn) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+    cuuint64_t strides[1] = {(cuuint64_t)(g.ldo * 2)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&ty, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, g.out[0], dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) g.tma_store = 1;
   }
-  auto kern = qgemm_kernel<CG, BN, STAGES, OutT, STAGED>;
+  auto kern = qgemm_kernel<CG, BN, STAGES, OutT, STAGED, MC>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
+  static int max_clusters = 0;   // co-resident clusters of this kernel (matters for 4-CTA clusters: 33, not 37)
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    max_clusters = num_sms / (CG * MC);
+    if (attr_err == cudaSuccess && MC > 1) {
+      cudaLaunchConfig_t oc = {};
+      oc.gridDim = dim3((unsigned)(num_sms / (CG * MC) * (CG * MC)), 1, 1);
+      oc.blockDim = dim3(NUM_THREADS, 1, 1);
+      oc.dynamicSmemBytes = L::DYN_BYTES;
+      cudaLaunchAttribute oa[1];
+      oa[0].id = cudaLaunchAttributeClusterDimension;
+      oa[0].val.clusterDim.x = CG * MC;
+      oa[0].val.clusterDim.y = 1;
+      oa[0].val.clusterDim.z = 1;
+      oc.attrs = oa;
+      oc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &oc) == cudaSuccess && n > 0) max_clusters = n;
+      else (void)cudaGetLastError();
+    }
   });
   if (attr_err != cudaSuccess)
     PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));
 
   const long long tiles = (long long)g.num_m_blocks * g.num_n_blocks;
-  long long clusters = num_sms / CG;
+  long long clusters = max_clusters;
   // Stream-K when whole tiles would leave SMs idle: fewer tiles than workers (small M: the
   // weight stream is spread over all SMs) or a ragged last wave.
   {
@@ -737,7 +885,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
     const long long units = tiles * g.num_k_blocks;
     const long long waves = (tiles + W - 1) / W;
     const double eff = (double)tiles / (double)(waves * W);
-    bool want = !STAGED && ((g_sk_mode == 1) || (g_sk_mode < 0 && eff < 0.95 && waves <= 8));
+    bool want = !STAGED && MC == 1 && ((g_sk_mode == 1) || (g_sk_mode < 0 && eff < 0.95 && waves <= 8));
     long long w_sk = W;
     if (units / 4 < w_sk) w_sk = units / 4;     // at least ~4 K blocks per worker
     if (w_sk < 2 || tiles % w_sk == 0) want = false;
@@ -754,13 +902,13 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   }
   if (g.sk_ws == nullptr && tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * CG), 1, 1);
+  cfg.gridDim = dim3((unsigned)(clusters * CG * MC), 1, 1);
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = L::DYN_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = CG;
+  attrs[0].val.clusterDim.x = CG * MC;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
   attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -774,6 +922,8 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
 
 int g_force_cfg = -1;  // test hook: see pq_debug_set_gemm_config
 int g_force_staged = 0;  // test hook: staged epilogue even for a single destination
+int g_epi_dbg = 0;       // profiling only: see GemmArgs::dbg
+int g_narrow_tiles = 1;  // heuristic may pick BLOCK_N in {240, 224, 208} (pq_debug_set_narrow_tiles)
 int g_prefetch_b = 0;    // L2 prefetch of the weight operand (pq_debug_set_prefetch): measured SLOWER, off
 
 template <typename OutT>
@@ -781,7 +931,8 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
                  int num_sms, cudaStream_t st) {
   // Tile configuration heuristic.
   //   cfg 0: 1-CTA 128x256   cfg 1: 2-CTA 256x256   cfg 2: 1-CTA 128x128   cfg 3: 1-CTA 128x64
-  //   cfg 4: 2-CTA 256x128
+  //   cfg 16: 4-CTA multicast cluster, 512x256 super-tiles (experiment: no faster, see README_r1.md)
+  //   cfg 4: 2-CTA 256x128   cfg 8/9/10: 2-CTA 256x{240,224,208}   cfg 11/12/13: 1-CTA 128x{240,224,208}
   if constexpr (!std::is_same<OutT, int32_t>::value) {
     if (g.n_out > 1 || g_force_staged) {
       // fused all-gather: coalesced (shared-memory staged) stores to every destination
@@ -802,7 +953,9 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
     else if (t2 <= num_sms) cfg = 2;
     else if (t0 <= num_sms) {
       cfg = 0;
-      if constexpr (!std::is_same<OutT, int32_t>::value) {   // one short-K wave: the epilogue is the kernel
+      // one short-K wave: the epilogue is the kernel.  16-bit outputs already leave through per-warp TMA
+      // stores (faster still: 4096x3072x768 12.9 us vs 14.5 us), fp32 outputs take the CTA-staged TMA path.
+      if constexpr (std::is_same<OutT, float>::value) {
         if ((g.K + BLOCK_K - 1) / BLOCK_K <= 16 && g.vec_ok && g_force_cfg < 0)
           return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
       }
@@ -813,10 +966,25 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
       const double eff0 = (double)t0 / (double)(w0 * num_sms), eff1 = (double)t1 / (double)(w1 * pairs);
       const long long kb = (g.K + BLOCK_K - 1) / BLOCK_K;
       cfg = (eff1 + 0.03 >= eff0 && w1 * kb > 80) ? 1 : 0;
+      // Narrower tiles (BLOCK_N = 240 / 224 / 208) when they cut the ragged last wave: the main loop
+      // of a worker lasts waves x BLOCK_N column-units, e.g. 2048 x 4096: 2 x 256 -> 2 x 240, and
+      // 2048 x 11008: 5 x 256 -> 5 x 240 (99 % of the SM-columns busy).  A narrower tile loads ~3 %
+      // more operand bytes per MMA, so it has to win by more than that.
+      if (g_narrow_tiles) {
+        const int cg = cfg == 1 ? 2 : 1;
+        const long long mt = (g.M + 128 * cg - 1) / (128 * cg), W = num_sms / cg;
+        const long long base = ((mt * ((g.N + 255) / 256) + W - 1) / W) * 256;
+        long long best = base * 97 / 100;
+        static const int bns[3] = {240, 224, 208};
+        for (int i = 0; i < 3; ++i) {
+          const long long cost = ((mt * ((g.N + bns[i] - 1) / bns[i]) + W - 1) / W) * bns[i];
+          if (cost < best) { best = cost; cfg = (cg == 2 ? 8 : 11) + i; }
+        }
+      }
       // Short-K, multi-wave problems are bound by the output write, not by the MMAs: the staged
       // epilogue (whole 256-byte row segments per store) is 9-14 % faster there (K <= 2048:
       // 4096x3072x768 21.0 -> 18.0 us, 8192x8192x1024 75.2 -> 68.9 us) and slower for long K.
-      if constexpr (!std::is_same<OutT, int32_t>::value) {
+      if constexpr (std::is_same<OutT, float>::value) {
         if (kb <= 16 && g.vec_ok && g_force_cfg < 0)
           return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
       }
@@ -830,6 +998,13 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
     case 4: return launch_cfg<2, 128, 8, OutT>(a, lda, b, ldb, g, num_sms, st);
     case 5: return launch_cfg<2, 256, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
     case 6: return launch_cfg<2, 256, 3, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 8: return launch_cfg<2, 240, 6, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 9: return launch_cfg<2, 224, 6, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 10: return launch_cfg<2, 208, 7, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 11: return launch_cfg<1, 240, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 12: return launch_cfg<1, 224, 4, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 13: return launch_cfg<1, 208, 5, OutT>(a, lda, b, ldb, g, num_sms, st);
+    case 16: return launch_cfg<2, 256, 6, OutT, false, 2>(a, lda, b, ldb, g, num_sms, st);
     default: PQ_FAIL(PQ_ERR_ARG, "qgemm: unknown tile config %d", cfg);
   }
 }
@@ -870,6 +1045,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   }
   g.tl = g_timeline;
   g.prefetch_b = g_prefetch_b;
+  g.dbg = g_epi_dbg;
   switch (out_dtype) {
     case PQ_BF16: return launch_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
     case PQ_F16: return launch_typed<__half>(a, lda, b, ldb, g, num_sms, stream);
@@ -891,7 +1067,7 @@ extern "C" void pq_debug_set_staged(int on) { pq::g_force_staged = on; }
 // (cudaOccupancyMaxActiveClusters); used to judge whether 4-CTA TMA multicast could pay.
 extern "C" int pq_debug_max_active_clusters(int cluster_size) {
   using namespace pq;
-  using L = SmemLayout<2, 256, 6, false>;
+  using L = SmemLayout<2, 256, 6, false, 2>;
   auto kern = qgemm_kernel<2, 256, 6, __nv_bfloat16, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) return -1;
   if (cluster_size > 8)
@@ -911,6 +1087,8 @@ extern "C" int pq_debug_max_active_clusters(int cluster_size) {
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return -2; }
   return n;
 }
+extern "C" void pq_debug_set_epilogue(int bits) { pq::g_epi_dbg = bits; }
+extern "C" void pq_debug_set_narrow_tiles(int on) { pq::g_narrow_tiles = on; }
 extern "C" void pq_debug_set_prefetch(int on) { pq::g_prefetch_b = on; }
 extern "C" void pq_debug_set_tma_store(int on) { pq::g_tma_store = on; }
 // device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null

@@ -27,6 +27,7 @@
 
 namespace pq {
 int g_force_tpr = 0, g_force_vpt = 0;   // test hook (pq_debug_set_quant_config)
+int g_weight_prefetch = 1;              // pq_qlinear: the act-quant kernel pulls the weights into L2
 namespace {
 
 using namespace qmath;
@@ -52,7 +53,7 @@ template <typename T, int TPR, int VPT>
 __global__ void __launch_bounds__((TPR > 256 ? TPR : 256))
 rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t ldx,
                          int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
-                         int scale_mode, float eps) {
+                         int scale_mode, float eps, const uint8_t* __restrict__ pf, long long pf_bytes) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
@@ -66,6 +67,19 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
   const bool row_ok = row < M;
 
   ptx::griddep_launch_dependents();
+  // Weight prefetch (pq_qlinear): the GEMM that follows streams `pf_bytes` of static int8 weights; this
+  // kernel leaves most of the DRAM bandwidth idle at activation sizes, so every CTA pulls its slice
+  // of them into L2 (no registers, no completion to wait for) before it waits for its own input.
+  if (pf != nullptr && tid == 0) {
+    const long long per = ((pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15LL;
+    long long off = (long long)blockIdx.x * per;
+    const long long end = (off + per < pf_bytes) ? off + per : (pf_bytes & ~15LL);
+    while (off < end) {
+      const uint32_t n = (uint32_t)((end - off < 16384) ? end - off : 16384);
+      ptx::prefetch_l2_bulk(pf + off, n);
+      off += n;
+    }
+  }
   ptx::griddep_wait();   // x may be produced, and xq still be read, by the previous kernel
   const T* xr = x + (row_ok ? row : 0) * ldx;
   uint4 v[VPT];
@@ -272,19 +286,21 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
 
 template <typename T, int TPR, int VPT>
 int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int64_t ldq,
-               float* s, const pq_quant_spec& spec, cudaStream_t st) {
+               float* s, const pq_quant_spec& spec, cudaStream_t st, const void* pf, long long pf_bytes) {
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
   const int64_t grid = (M + ROWS - 1) / ROWS;
   PQ_CUDA(launch_pdl(rowwise_quant_vec_kernel<T, TPR, VPT>, (unsigned)grid, THREADS, st,
-                     (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
+                     (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps,
+                     (const uint8_t*)pf, pf_bytes));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;
 }
 
 template <typename T>
 int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq,
-             float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st) {
+             float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st,
+             const void* pf, long long pf_bytes) {
   constexpr int EPV = VecTraits<T>::EPV;
   if (M == 0) return PQ_OK;
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
@@ -333,7 +349,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
     if (score < best_score) { best_score = score; best_tpr = tpr; best_vpt = vpt; }
   }
   if (g_force_tpr > 0 && g_force_vpt > 0 && g_force_tpr * g_force_vpt >= nvec) { best_tpr = g_force_tpr; best_vpt = g_force_vpt; }
-#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st);
+#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes);
 #define PQ_CASE_T(TPR) PQ_CASE_V(TPR, 2) PQ_CASE_V(TPR, 3) PQ_CASE_V(TPR, 4) PQ_CASE_V(TPR, 6) PQ_CASE_V(TPR, 8)
   PQ_CASE_T(32) PQ_CASE_T(64) PQ_CASE_T(128) PQ_CASE_T(256) PQ_CASE_T(512) PQ_CASE_T(1024)
 #undef PQ_CASE_T
@@ -345,7 +361,9 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
 
 int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
                          int8_t* xq, int64_t ldq, float* s, int transpose,
-                         const pq_quant_spec& spec, cudaStream_t stream) {
+                         const pq_quant_spec& spec, cudaStream_t stream,
+                         const void* prefetch, long long prefetch_bytes) {
+  if (((uintptr_t)prefetch & 15) || prefetch_bytes < 16 || !g_weight_prefetch) { prefetch = nullptr; prefetch_bytes = 0; }
   if (M < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: bad shape M=%lld K=%lld", (long long)M, (long long)K);
   if (M > 0 && (!x || !xq || !s)) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: null pointer");
   if (ldx < K) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: ldx=%lld < K=%lld", (long long)ldx, (long long)K);
@@ -356,9 +374,9 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
   if (spec.qmin != -128 && spec.qmin != -127)
     PQ_FAIL(PQ_ERR_ARG, "rowwise quant: qmin must be -128 or -127");
   switch (x_dtype) {
-    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream);
-    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream);
-    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream);
+    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes);
+    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes);
+    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes);
     default: PQ_FAIL(PQ_ERR_ARG, "rowwise quant: unsupported dtype %d", x_dtype);
   }
 }
@@ -367,3 +385,4 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
 
 // Test/bench hook: force (threads per row, 16-byte vectors per thread) of the vectorised kernel; 0,0 = heuristic.
 extern "C" void pq_debug_set_quant_config(int tpr, int vpt) { pq::g_force_tpr = tpr; pq::g_force_vpt = vpt; }
+extern "C" void pq_debug_set_weight_prefetch(int on) { pq::g_weight_prefetch = on; }

@@ -190,6 +190,22 @@ def qlinear(x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tensor, bias: Optional
     return y.reshape(*lead, wq.shape[0])
 
 
+def qlinear_into(x2: torch.Tensor, wq_storage: torch.Tensor, in_features: int, s_w: torch.Tensor,
+                 bias: Optional[torch.Tensor], y: torch.Tensor, xq_ws: torch.Tensor, sx_ws: torch.Tensor,
+                 spec: Optional[QuantSpec] = None) -> torch.Tensor:
+    """One `pq_qlinear` call (act-quant launch + GEMM launch, or the fused decode kernel) on caller-owned
+    buffers: x2 [M,K] row-major, wq_storage [N, ld>=K] int8 with a 16-byte row stride, y [M,N],
+    xq_ws [M, ld16(K)] int8 and sx_ws [M] fp32 scratch.  No allocation, no checks beyond the C ABI's."""
+    M, N, K = x2.shape[0], wq_storage.shape[0], in_features
+    if M:
+        rc = _lib.lib().pq_qlinear(x2.data_ptr(), _DT[x2.dtype], x2.stride(0), wq_storage.data_ptr(), wq_storage.stride(0),
+                                   s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                   y.data_ptr(), _DT[y.dtype], y.stride(0), xq_ws.data_ptr(), sx_ws.data_ptr(), M, N, K,
+                                   _specp(spec), _stream())
+        _lib.check(rc, "pq_qlinear")
+    return y
+
+
 def dequantize(q: torch.Tensor, s: torch.Tensor, axis: int = 0, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """out[r,c] = q[r,c] * s[r] (axis=0) or q[r,c] * s[c] (axis=1)."""
     _require_cuda(q, "q")

@@ -70,12 +70,7 @@ class DynamicQuantLinear(nn.Module):
         if M:
             xq = torch.empty((M, wq.shape[1]), dtype=torch.int8, device=x.device)
             sx = torch.empty((M,), dtype=torch.float32, device=x.device)
-            bias = self.bias
-            rc = _lib.lib().pq_qlinear(x2.data_ptr(), F._DT[x2.dtype], x2.stride(0), wq.data_ptr(), wq.stride(0),
-                                       self.weight_scale.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                       y.data_ptr(), F._DT[out_dtype], N, xq.data_ptr(), sx.data_ptr(), M, N, K,
-                                       F._specp(self.spec), F._stream())
-            _lib.check(rc, "pq_qlinear")
+            F.qlinear_into(x2, wq, K, self.weight_scale, self.bias, y, xq, sx, self.spec)
         return y.reshape(*x.shape[:-1], N)
 
     def dequantized_weight(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:

@@ -16,7 +16,7 @@ import protoquant_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = [-1, 0, 1, 2, 3, 4]   # -1 = heuristic (small-M kernel for M <= 64); see launch_typed() in csrc/qgemm_tcgen05.cu
+CONFIGS = [-1, 0, 1, 2, 3, 4, 8, 9, 10, 11, 12, 13, 16]   # 8-13 = narrow tiles (BLOCK_N 240/224/208), 16 = 4-CTA multicast cluster; -1 = heuristic (small-M kernel for M <= 64); see launch_typed() in csrc/qgemm_tcgen05.cu
 
 
 @pytest.fixture(autouse=True)
@@ -52,7 +52,7 @@ def test_int32_accumulators_bit_exact(cfg, shape, sk):
 
 
 @pytest.mark.parametrize("sk", [0, 1])
-@pytest.mark.parametrize("cfg", [0, 1, 4])
+@pytest.mark.parametrize("cfg", [0, 1, 4, 8, 11, 16])
 @pytest.mark.parametrize("shape", [(2048, 4096, 4096), (2048, 11008, 4096), (2048, 4096, 11008),
                                    (4096, 3072, 768), (1024, 3584, 8192), (256, 8192, 28672)])
 def test_int32_full_size_shapes(cfg, shape, sk):
@@ -97,7 +97,7 @@ def test_persistent_scheduler_many_tiles():
     a, b = rand_i8((M, K), 9), rand_i8((N, K), 10)
     for sk in (0, 1):
         pq.lib().pq_debug_set_streamk(sk)
-        for cfg in (0, 1, 2, 3, 4):
+        for cfg in (0, 1, 2, 3, 4, 8, 9, 10, 11, 12, 13, 16):
             pq.lib().pq_debug_set_gemm_config(cfg)
             assert torch.equal(pq.qgemm_i32(a.cuda(), b.cuda()).cpu(), cpu_int_mm(a, b)), (cfg, sk)
 
@@ -135,7 +135,7 @@ def _bits(t):
 
 
 @pytest.mark.parametrize("sk", [-1, 1])
-@pytest.mark.parametrize("cfg", [-1, 0, 1, 3])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 3, 8, 13, 16])
 @pytest.mark.parametrize("out", [(torch.bfloat16, "bf16"), (torch.float16, "f16"), (torch.float32, "f32")])
 @pytest.mark.parametrize("shape,use_bias", [((256, 512, 512), True), ((100, 264, 272), False),
                                             ((16, 4096, 4096), True), ((700, 1000, 768), True)])

