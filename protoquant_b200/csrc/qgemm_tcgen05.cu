@@ -465,6 +465,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (row < g.M) sx = __ldg(g.s_x + row);
         named_bar_sync(1, EPI_THREADS);
       }
+      // (Letting one lane per warp poll and the others pass the completed phase afterwards was measured
+      // 2-3 % SLOWER under the power cap: 8192^3 2576 vs 2636 TOPS sustained -- all lanes wait.)
       mbar_wait(bar_tfull + as * 8, aphase);
       tc_fence_after();
       __syncwarp();
@@ -762,7 +764,7 @@ struct SkPool {
 SkPool g_sk_pool[64];
 unsigned long long* g_timeline = nullptr;
 int g_tma_store = 1;     // staged epilogue uses TMA bulk stores when it can (pq_debug_set_tma_store)
-int g_sk_mode = 0;   // 0 never (default until the fix-up path is cheap enough), 1 whenever legal, -1 heuristic
+int g_sk_mode = -1;  // -1 heuristic (default: single-wave long-K problems only), 0 never, 1 whenever legal
 
 bool sk_alloc_slot(SkPool& pool, int num_sms) {
   if (pool.count >= SK_MAX_SLOTS) return false;
@@ -885,7 +887,13 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
     const long long units = tiles * g.num_k_blocks;
     const long long waves = (tiles + W - 1) / W;
     const double eff = (double)tiles / (double)(waves * W);
-    bool want = !STAGED && MC == 1 && ((g_sk_mode == 1) || (g_sk_mode < 0 && eff < 0.95 && waves <= 8));
+    // Heuristic (mode -1, default): stream-K pays only when the whole problem is less than one wave of
+    // tiles and K is long -- each worker then streams K/S of a tile and the int32 fix-up (one partial
+    // write + read per worker) is small next to it.  Measured (profiles/README_r1.md): 128x1024x16384
+    // 27.7 -> 15.4 us, 128x4096x11008 20.0 -> 17.1 us, but 128x4096x4096 9.6 -> 12.5 us and
+    // 2048x4096x4096 29.2 -> 35.9 us, hence K >= 8192 and a single wave.
+    (void)eff;
+    bool want = !STAGED && MC == 1 && ((g_sk_mode == 1) || (g_sk_mode < 0 && waves == 1 && tiles < W && g.num_k_blocks >= 64));
     long long w_sk = W;
     if (units / 4 < w_sk) w_sk = units / 4;     // at least ~4 K blocks per worker
     if (w_sk < 2 || tiles % w_sk == 0) want = false;
@@ -1029,7 +1037,10 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   int rc = check_device(&num_sms);
   if (rc) return rc;
   // Decode-sized batches take the swap-AB weight-streaming kernel (qgemm_smallm.cu).
-  if (M <= 64 && n_out == 1 && !g_force_staged && g_sk_mode != 1 && (g_force_cfg < 0 || g_force_cfg == 7))
+  // ... unless K is short: the cluster split-K machinery then costs more than it saves (64 x 4096 x 1024:
+  // 11.4 us vs 5.0 us with 128x64 tiles; 64 x 4096 x 2048: 9.2 vs 6.4 us; 48 x 4096 x 4096: 8.3 vs 9.4 us).
+  const bool smallm_pays = !(M > 32 && K <= 2048);
+  if (M <= 64 && n_out == 1 && !g_force_staged && g_sk_mode != 1 && ((g_force_cfg < 0 && smallm_pays) || g_force_cfg == 7))
     return launch_qgemm_smallm(a, lda, b, ldb, s_x, s_w, bias, outs[0], out_dtype, ldo, M, N, K, num_sms, stream);
   if (g_force_cfg == 7) PQ_FAIL(PQ_ERR_ARG, "qgemm: config 7 (small-M kernel) needs M <= 64");
   GemmArgs g = {};

@@ -36,6 +36,10 @@ def cpu_int_mm(a, b):
     return torch.from_numpy(O.int_mm(a.numpy(), b.numpy()))
 
 
+def _bits(t):
+    return t.view(torch.int32 if t.dtype == torch.float32 else torch.int16)
+
+
 @pytest.mark.parametrize("sk", [0, 1])   # 0 = data-parallel tiles only, 1 = stream-K whenever legal
 @pytest.mark.parametrize("cfg", CONFIGS)
 @pytest.mark.parametrize("shape", [
@@ -64,6 +68,26 @@ def test_int32_full_size_shapes(cfg, shape, sk):
     a, b = rand_i8((M, K), 3), rand_i8((N, K), 4)
     got = pq.qgemm_i32(a.cuda(), b.cuda())
     assert torch.equal(got.cpu(), cpu_int_mm(a, b))
+
+
+@pytest.mark.parametrize("shape", [(128, 1024, 16384), (96, 4096, 11008), (256, 2048, 8192), (64, 4096, 1024),
+                                   (40, 1000, 2048), (64, 4096, 4096), (128, 4096, 4096)])
+def test_default_heuristics_bit_exact(shape):
+    """What launch_qgemm picks by itself: stream-K for single-wave long-K problems, 128x64 tiles instead of
+    the small-M kernel for short K, the small-M kernel otherwise -- accumulators and epilogue bit-exact."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(61)
+    xq, wq = rand_i8((M, K), 62), rand_i8((N, K), 63)
+    ref = cpu_int_mm(xq, wq)
+    for _ in range(2):      # twice: the stream-K counters must be clean for the second launch
+        assert torch.equal(pq.qgemm_i32(xq.cuda(), wq.cuda()).cpu(), ref)
+    s_x = torch.rand(M, generator=g) * 0.1 + 1e-3
+    s_w = torch.rand(N, generator=g) * 0.01 + 1e-4
+    bias = torch.randn(N, generator=g)
+    for dt, name in ((torch.bfloat16, "bf16"), (torch.float32, "f32")):
+        y = pq.qgemm(xq.cuda(), s_x.cuda(), wq.cuda(), s_w.cuda(), bias.cuda(), dt)
+        want = O.cast_out(O.dequant_epilogue(ref.numpy(), s_x.numpy(), s_w.numpy(), bias.numpy()), name)
+        assert torch.equal(_bits(y.cpu()), _bits(want))
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "int_mm_*.npz"))))
@@ -128,10 +152,6 @@ def test_streamk_repeated_launches_and_cuda_graph_replay():
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(y, ref.float())
-
-
-def _bits(t):
-    return t.view(torch.int32 if t.dtype == torch.float32 else torch.int16)
 
 
 @pytest.mark.parametrize("sk", [-1, 1])

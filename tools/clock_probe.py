@@ -5,6 +5,7 @@ import torch, pynvml
 import protoquant_b200 as pq
 M, N, K, cfg = (int(v) for v in sys.argv[1:5]); secs = float(sys.argv[5])
 pq.lib().pq_debug_set_gemm_config(cfg)
+pq.lib().pq_debug_set_epilogue(int(os.environ.get("PQ_EPI", "0")))
 a = torch.randint(-128, 128, (M, K), dtype=torch.int8, device="cuda")
 b = torch.randint(-128, 128, (N, K), dtype=torch.int8, device="cuda")
 sx = torch.rand(M, device="cuda"); sw = torch.rand(N, device="cuda")
@@ -37,4 +38,4 @@ ms = e0.elapsed_time(e1) / n
 half = samples[len(samples)//2:]
 clk = sorted(x[0] for x in half); pw = sorted(x[1] for x in half); rs = 0
 for x in half: rs |= x[2]
-print(f"M={M} N={N} K={K} cfg={cfg}: {ms*1e3:.1f} us/launch {2*M*N*K/ms/1e9:.0f} TOPS sustained over {secs}s; SM clock median {clk[len(clk)//2]} MHz (min {clk[0]}), power median {pw[len(pw)//2]:.0f} W, reasons 0x{rs:x}, samples {len(half)}")
+print(f"M={M} N={N} K={K} cfg={cfg} epi={os.environ.get('PQ_EPI', '0')}: {ms*1e3:.1f} us/launch {2*M*N*K/ms/1e9:.0f} TOPS sustained over {secs}s; SM clock median {clk[len(clk)//2]} MHz (min {clk[0]}), power median {pw[len(pw)//2]:.0f} W, reasons 0x{rs:x}, samples {len(half)}")
