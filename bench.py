@@ -455,6 +455,12 @@ def run_ours(args):
             decode = decode_leg(pq, F, torch, dev, peaks)
         except Exception as ex:
             decode = {"error": repr(ex)[:200]}
+    fused = None
+    if rank == 0:
+        try:
+            fused = fused_producer_leg(F, torch, dev, peaks)
+        except Exception as ex:
+            fused = {"error": repr(ex)[:200]}
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1) else None
     clocks = sampler.result()
     if rank == 0:
@@ -469,7 +475,7 @@ def run_ours(args):
             "tokens_per_s": world * M_TOKENS / (ms_per_step * 1e-3),
             "frac_of_nominal_int8": value / world / NOMINAL_INT8_TOPS,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "sharded_70b": sharded, "decode_16tok": decode,
+            "clocks": clocks, "sharded_70b": sharded, "decode_16tok": decode, "fused_producers": fused,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -522,6 +528,52 @@ def decode_leg(pq, F, torch, dev, peaks):
         res[name] = {"us_per_forward": us, "tokens_per_s": 16 / (us * 1e-6), "achieved_gbs": gbs,
                      "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
         del mods
+    return res
+
+
+def fused_producer_leg(F, torch, dev, peaks):
+    """SURVEY.md §8f-2: RMSNorm -> int8 and silu(gate)*up -> int8 written by one kernel each (HBM-bound;
+    algorithmic bytes per row 3K+4 and 5K+4 for bf16), at a streaming size (>> L2) and at the step's size."""
+    res = {}
+
+    def timed(fn, iters):
+        fn(0)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn(0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                fn(i)
+        g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (3 * iters)
+
+    for label, M, K in (("rmsnorm_quant_stream", 131072, 4096), ("rmsnorm_quant_2048tok", 2048, 4096)):
+        nb = max(1, min(8, int(600e6 // (M * K * 2))))
+        xs = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(nb)]
+        w = torch.ones(K, dtype=torch.bfloat16, device=dev)
+        q, s = F.alloc_q(M, K, dev), torch.empty(M, dtype=torch.float32, device=dev)
+        ms = timed(lambda i: F.rmsnorm_quant(xs[i % nb], w, out=(q, s)), 10 if M > 10000 else 50)
+        gbs = M * (3 * K + 4) / (ms * 1e-3) / 1e9
+        res[label] = {"shape": [M, K], "us": ms * 1e3, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+        del xs
+    for label, M, K in (("silu_mul_quant_stream", 32768, 11008), ("silu_mul_quant_2048tok", 2048, 11008)):
+        nb = max(1, min(8, int(600e6 // (M * K * 4))))
+        gs = [torch.randn(M, 2 * K, device=dev).to(torch.bfloat16) for _ in range(nb)]
+        q, s = F.alloc_q(M, K, dev), torch.empty(M, dtype=torch.float32, device=dev)
+        ms = timed(lambda i: F.act_mul_quant(gs[i % nb][:, :K], gs[i % nb][:, K:], act="silu", out=(q, s)), 10 if M > 10000 else 50)
+        gbs = M * (5 * K + 4) / (ms * 1e-3) / 1e9
+        res[label] = {"shape": [M, K], "us": ms * 1e3, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+        del gs
     return res
 
 

@@ -119,6 +119,30 @@ int pq_qlinear(const void* x, int x_dtype, int64_t ldx,
                int64_t M, int64_t N, int64_t K,
                const pq_quant_spec* spec, void* stream);
 
+/* SURVEY §8f-2 — producer-fused quantizers: the op in front of a dynamic-quant linear writes the int8
+ * operand and its per-token scale directly.  `y` / `h` (nullable) additionally receives the tensor the
+ * unfused op would have stored (dtype of the input); (xq, s_x) is exactly the row-wise quantisation
+ * (pq_act_quant arithmetic, same `spec`) of that tensor.  Rows of x / gamma / beta / y / gate / up / h must be
+ * 16-byte aligned and K a multiple of 16 / sizeof(dtype) (PQ_ERR_UNSUPPORTED / PQ_ERR_ALIGN otherwise).
+ *
+ * pq_norm_quant: beta == NULL  ->  RMSNorm   y = T(gamma * T(x * rsqrt(mean(x^2) + eps)))      (Llama)
+ *                beta != NULL  ->  LayerNorm y = T((x - mean) * rsqrt(var + eps) * gamma + beta) (BERT)
+ *   x [M,K] row stride ldx (elements); gamma, beta [K] of x_dtype; statistics in fp32. */
+int pq_norm_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
+                  const void* gamma, const void* beta, float eps,
+                  int8_t* xq, int64_t ldq, float* s_x, void* y, int64_t ldy,
+                  const pq_quant_spec* spec, void* stream);
+
+enum pq_act { PQ_ACT_IDENTITY = 0, PQ_ACT_SILU = 1, PQ_ACT_GELU = 2, PQ_ACT_GELU_TANH = 3 };
+
+/* pq_act_mul_quant: h = T(T(act(gate)) * up)   (up != NULL: Llama MLP, act = PQ_ACT_SILU)
+ *                   h = T(act(gate))           (up == NULL: BERT FFN, act = PQ_ACT_GELU)
+ *   gate, up [M,K] of `dtype`, row strides ldg / ldu (elements). */
+int pq_act_mul_quant(const void* gate, const void* up, int dtype, int act,
+                     int64_t M, int64_t K, int64_t ldg, int64_t ldu,
+                     int8_t* hq, int64_t ldq, float* s_h, void* h, int64_t ldh,
+                     const pq_quant_spec* spec, void* stream);
+
 /* Host-buffer convenience API (what bench.py's "e2e" number goes through).
  * A pq_linear owns device copies of (Wq, s_w, bias), a device activation/output
  * workspace for up to max_tokens rows, and a private stream. */

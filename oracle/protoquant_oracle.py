@@ -169,6 +169,44 @@ def qlinear(x, wq: np.ndarray, s_w: np.ndarray, bias: Optional[np.ndarray] = Non
     return y.reshape(*lead, wq.shape[0])
 
 
+# ---- producer ops in front of the path ------------------------------
+# fp64 references of the tensors the fused kernels emit: the floating-point half of their parity
+# (tolerance stated in tests/test_gpu_fused.py); the integer half is quantize_rowwise() of the
+# emitted tensor, bit-exact.
+def rmsnorm_ref(x, gamma, eps: float) -> np.ndarray:
+    """Llama RMSNorm, exact arithmetic: gamma * x * rsqrt(mean(x^2) + eps)."""
+    x64 = to_f32(x).astype(np.float64)
+    g64 = to_f32(gamma).astype(np.float64)
+    r = 1.0 / np.sqrt(np.mean(x64 * x64, axis=-1, keepdims=True) + eps)
+    return x64 * r * g64
+
+
+def layernorm_ref(x, gamma, beta, eps: float) -> np.ndarray:
+    x64 = to_f32(x).astype(np.float64)
+    mu = np.mean(x64, axis=-1, keepdims=True)
+    var = np.mean((x64 - mu) ** 2, axis=-1, keepdims=True)
+    return (x64 - mu) / np.sqrt(var + eps) * to_f32(gamma).astype(np.float64) + to_f32(beta).astype(np.float64)
+
+
+def act_ref(x64: np.ndarray, act: str) -> np.ndarray:
+    import math
+    if act == "identity":
+        return x64
+    if act == "silu":
+        return x64 / (1.0 + np.exp(-x64))
+    if act == "gelu":
+        erf = np.vectorize(math.erf)
+        return 0.5 * x64 * (1.0 + erf(x64 / math.sqrt(2.0)))
+    if act == "gelu_tanh":
+        return 0.5 * x64 * (1.0 + np.tanh(math.sqrt(2.0 / math.pi) * (x64 + 0.044715 * x64 ** 3)))
+    raise ValueError(act)
+
+
+def act_mul_ref(gate, up=None, act: str = "silu") -> np.ndarray:
+    a = act_ref(to_f32(gate).astype(np.float64), act)
+    return a if up is None else a * to_f32(up).astype(np.float64)
+
+
 # ---- torch-threaded variant used only as the timed CPU baseline (bench.py) ----------
 def qlinear_torch_cpu(x_t, wq_t_kn, s_w_t, bias_t, out_dtype):
     """Same math as `qlinear` written with torch CPU ops so it uses every host thread.

@@ -4,8 +4,8 @@ Python surface over the C ABI in include/protoquant_b200.h.
 No Triton, no backend dispatch, no CPU fallback.
 """
 from ._lib import ProtoquantError, launch_count, lib
-from .functional import (DEFAULT_SPEC, QuantSpec, dequantize as dequantize_tensor, qgemm, qgemm_i32, qlinear,
-                         quantize_act, quantize_weight)
+from .functional import (DEFAULT_SPEC, QuantSpec, act_mul_quant, dequantize as dequantize_tensor, layernorm_quant,
+                         norm_quant, qgemm, qgemm_i32, qlinear, quantize_act, quantize_weight, rmsnorm_quant)
 from .modules import DynamicQuantLinear, swap_linear
 from .qtensor import QTensor, dequantize, quantize
 from .sharded import ShardedDynamicQuantLinear, maybe_shard, shard_bounds
@@ -14,6 +14,7 @@ __version__ = "0.1.0"
 __all__ = [
     "ProtoquantError", "launch_count", "lib", "QuantSpec", "DEFAULT_SPEC",
     "quantize_act", "quantize_weight", "qgemm", "qgemm_i32", "qlinear", "dequantize_tensor",
+    "norm_quant", "rmsnorm_quant", "layernorm_quant", "act_mul_quant",
     "QTensor", "quantize", "dequantize", "DynamicQuantLinear", "swap_linear",
     "ShardedDynamicQuantLinear", "maybe_shard", "shard_bounds",
 ]

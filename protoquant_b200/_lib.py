@@ -15,12 +15,14 @@ LIB_PATH = os.path.join(_HERE, "libprotoquant_b200.so")
 
 PQ_F32, PQ_F16, PQ_BF16, PQ_I32 = 0, 1, 2, 3
 PQ_DIV, PQ_RCP_MUL, PQ_INV_SCALE = 0, 1, 2
+PQ_ACT_IDENTITY, PQ_ACT_SILU, PQ_ACT_GELU, PQ_ACT_GELU_TANH = 0, 1, 2, 3
 
 # every symbol include/protoquant_b200.h declares (tests/test_abi.py checks the .so exports them)
 EXPORTS = (
     "pq_version", "pq_last_error", "pq_launch_count", "pq_act_quant", "pq_weight_quant",
     "pq_qgemm", "pq_qgemm_multi", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
     "pq_linear_create", "pq_linear_forward_host", "pq_linear_destroy",
+    "pq_norm_quant", "pq_act_mul_quant",
 )
 
 
@@ -66,6 +68,10 @@ def _declare(lib):
     lib.pq_linear_forward_host.argtypes = [vp, vp, vp, i64]
     lib.pq_linear_destroy.restype = None
     lib.pq_linear_destroy.argtypes = [vp]
+    lib.pq_norm_quant.restype = i32
+    lib.pq_norm_quant.argtypes = [vp, i32, i64, i64, i64, vp, vp, c.c_float, vp, i64, vp, vp, i64, specp, vp]
+    lib.pq_act_mul_quant.restype = i32
+    lib.pq_act_mul_quant.argtypes = [vp, vp, i32, i32, i64, i64, i64, i64, vp, i64, vp, vp, i64, specp, vp]
     if hasattr(lib, "pq_debug_set_quant_config"):
         lib.pq_debug_set_quant_config.restype = None
         lib.pq_debug_set_quant_config.argtypes = [i32, i32]

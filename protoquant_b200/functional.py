@@ -206,6 +206,89 @@ def qlinear_into(x2: torch.Tensor, wq_storage: torch.Tensor, in_features: int, s
     return y
 
 
+_ACTS = {"identity": _lib.PQ_ACT_IDENTITY, "silu": _lib.PQ_ACT_SILU, "gelu": _lib.PQ_ACT_GELU,
+         "gelu_tanh": _lib.PQ_ACT_GELU_TANH}
+
+
+def _fused_out(M: int, K: int, like: torch.Tensor, return_float: bool, out):
+    if out is not None:
+        xq, s_x = out
+    else:
+        xq = alloc_q(M, K, like.device)
+        s_x = torch.empty((M,), dtype=torch.float32, device=like.device)
+    y = torch.empty((M, K), dtype=like.dtype, device=like.device) if return_float else None
+    return xq, s_x, y
+
+
+def norm_quant(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, eps: float = 1e-6,
+               spec: Optional[QuantSpec] = None, return_normed: bool = False,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """Fused RMSNorm (bias=None, Llama) / LayerNorm (bias given, BERT) + per-token int8 quantisation
+    (SURVEY.md §8f-2): x[..., K] -> (xq int8 [M,K], s_x fp32 [M]) ready for `qgemm`, plus the normalised
+    tensor itself (dtype of x) when `return_normed`.  (xq, s_x) is bit-identical to
+    `quantize_act(normed)`; one read of x instead of a norm kernel + a quantizer kernel."""
+    _require_cuda(x, "x")
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {x.dtype}")
+    K = x.shape[-1]
+    x2 = _rows2d(x.reshape(-1, K))
+    M = x2.shape[0]
+    w = weight.to(device=x.device, dtype=x.dtype).contiguous()
+    b = bias.to(device=x.device, dtype=x.dtype).contiguous() if bias is not None else None
+    if w.numel() != K or (b is not None and b.numel() != K):
+        raise ValueError("norm weight / bias must have K elements")
+    xq, s_x, y = _fused_out(M, K, x2, return_normed, out)
+    if M:
+        rc = _lib.lib().pq_norm_quant(x2.data_ptr(), _DT[x2.dtype], M, K, x2.stride(0), w.data_ptr(),
+                                      b.data_ptr() if b is not None else None, float(eps),
+                                      xq.data_ptr(), xq.stride(0), s_x.data_ptr(),
+                                      y.data_ptr() if y is not None else None, K, _specp(spec), _stream())
+        _lib.check(rc, "pq_norm_quant")
+    return (xq, s_x, y.reshape(x.shape)) if return_normed else (xq, s_x)
+
+
+def rmsnorm_quant(x, weight, eps: float = 1e-6, **kw):
+    return norm_quant(x, weight, None, eps, **kw)
+
+
+def layernorm_quant(x, weight, bias, eps: float = 1e-5, **kw):
+    return norm_quant(x, weight, bias, eps, **kw)
+
+
+def act_mul_quant(gate: torch.Tensor, up: Optional[torch.Tensor] = None, act: str = "silu",
+                  spec: Optional[QuantSpec] = None, return_float: bool = False,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """Fused act(gate) [* up] + per-token int8 quantisation: the Llama MLP's `silu(gate) * up` (or BERT's
+    `gelu(x)`) written straight as the int8 operand of the down projection.  gate / up may be column
+    slices of one [M, 2K] GEMM output (any row stride that keeps rows 16-byte aligned)."""
+    _require_cuda(gate, "gate")
+    if gate.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {gate.dtype}")
+    if act not in _ACTS:
+        raise ValueError(f"act must be one of {sorted(_ACTS)}")
+    K = gate.shape[-1]
+    g2 = gate.reshape(-1, K) if gate.dim() != 2 else gate
+    if g2.stride(1) != 1:
+        g2 = g2.contiguous()
+    u2 = None
+    if up is not None:
+        _require_cuda(up, "up")
+        if up.shape != gate.shape or up.dtype != gate.dtype:
+            raise ValueError("up must match gate in shape and dtype")
+        u2 = up.reshape(-1, K) if up.dim() != 2 else up
+        if u2.stride(1) != 1:
+            u2 = u2.contiguous()
+    M = g2.shape[0]
+    hq, s_h, h = _fused_out(M, K, g2, return_float, out)
+    if M:
+        rc = _lib.lib().pq_act_mul_quant(g2.data_ptr(), u2.data_ptr() if u2 is not None else None, _DT[g2.dtype],
+                                         _ACTS[act], M, K, g2.stride(0), u2.stride(0) if u2 is not None else 0,
+                                         hq.data_ptr(), hq.stride(0), s_h.data_ptr(),
+                                         h.data_ptr() if h is not None else None, K, _specp(spec), _stream())
+        _lib.check(rc, "pq_act_mul_quant")
+    return (hq, s_h, h.reshape(gate.shape)) if return_float else (hq, s_h)
+
+
 def dequantize(q: torch.Tensor, s: torch.Tensor, axis: int = 0, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """out[r,c] = q[r,c] * s[r] (axis=0) or q[r,c] * s[c] (axis=1)."""
     _require_cuda(q, "q")

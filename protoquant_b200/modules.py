@@ -12,6 +12,7 @@ from torch import nn
 
 from . import _lib
 from . import functional as F
+from .qtensor import QTensor
 
 
 class DynamicQuantLinear(nn.Module):
@@ -53,7 +54,20 @@ class DynamicQuantLinear(nn.Module):
             m.bias.copy_(linear.bias.detach().to(torch.float32))
         return m
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_quantized(self, xq: torch.Tensor, s_x: torch.Tensor, out_dtype: Optional[torch.dtype] = None,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """GEMM + dequant epilogue only, for an input that is already per-token int8 (a QTensor's payload,
+        or the output of `rmsnorm_quant` / `act_mul_quant`): xq int8 [M,K], s_x fp32 [M] -> y [M,N]."""
+        return F.qgemm(xq, s_x, self.qweight, self.weight_scale, self.bias,
+                       out_dtype or self.out_dtype or torch.bfloat16, out=out)
+
+    def forward(self, x) -> torch.Tensor:
+        # A QTensor (or an (int8, scale) pair) is an activation that is already quantised per token.
+        if isinstance(x, QTensor):
+            y = self.forward_quantized(x.data, x.scale, self.out_dtype or x.orig_dtype)
+            return y.reshape(*x.orig_shape[:-1], self.out_features)
+        if isinstance(x, tuple) and len(x) == 2:
+            return self.forward_quantized(x[0], x[1])
         # Lean path: one C-ABI call (pq_qlinear = act-quant launch + GEMM launch), three allocations.
         K, N = self.in_features, self.out_features
         if (not x.is_cuda) or x.dtype not in F._DT or x.shape[-1] != K:

@@ -61,6 +61,8 @@ def test_no_cpu_fallback_in_the_c_abi():
     h = ctypes.c_void_p()
     rc = lib.pq_linear_create(ctypes.byref(h), p, 0, 1, 16, None, 1, 0, 2, None)
     assert rc == 3
+    assert lib.pq_norm_quant(p, 2, 1, 16, 16, p, None, 1e-6, p, 16, p, None, 0, None, None) == 3
+    assert lib.pq_act_mul_quant(p, p, 2, 1, 1, 16, 16, 16, p, 16, p, None, 0, None, None) == 3
 
 
 def test_python_surface_rejects_cpu_tensors():

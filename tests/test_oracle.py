@@ -172,3 +172,19 @@ def test_torch_threaded_baseline_matches_oracle():
     y0 = O.qlinear(x, wq, sw, b.numpy(), out_dtype="bf16")
     y1 = O.qlinear_torch_cpu(x, torch.from_numpy(wq).t(), torch.from_numpy(sw), b, torch.bfloat16)
     assert torch.equal(y0, y1)
+
+
+def test_producer_op_references_match_torch_float64():
+    """oracle.rmsnorm_ref / layernorm_ref / act_mul_ref (the fp64 references of tests/test_gpu_fused.py)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(6, 96, generator=g, dtype=torch.float64)
+    w = torch.randn(96, generator=g, dtype=torch.float64)
+    b = torch.randn(96, generator=g, dtype=torch.float64)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    assert np.allclose(O.rmsnorm_ref(x.float(), w.float(), 1e-6), ref.numpy(), rtol=1e-5, atol=1e-6)
+    ln = torch.nn.functional.layer_norm(x, (96,), w, b, 1e-5)
+    assert np.allclose(O.layernorm_ref(x.float(), w.float(), b.float(), 1e-5), ln.numpy(), rtol=1e-5, atol=1e-5)
+    for act, fn in (("silu", torch.nn.functional.silu), ("gelu", torch.nn.functional.gelu),
+                    ("gelu_tanh", lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
+        assert np.allclose(O.act_mul_ref(x.float(), w.expand(6, 96).float(), act), (fn(x) * w).numpy(), rtol=1e-5, atol=1e-6)
+        assert np.allclose(O.act_mul_ref(x.float(), None, act), fn(x).numpy(), rtol=1e-5, atol=1e-6)
