@@ -143,6 +143,29 @@ int pq_act_mul_quant(const void* gate, const void* up, int dtype, int act,
                      int8_t* hq, int64_t ldq, float* s_h, void* h, int64_t ldh,
                      const pq_quant_spec* spec, void* stream);
 
+/* SURVEY §8f-3 — row-parallel (K-split) sharding with a fused GEMM + reduce-scatter.  Rank r holds columns
+ * [k_lo, k_hi) of x and of Wq.  The per-token scale needs the maximum over the WHOLE row, so each rank takes
+ * pq_row_absmax of its slice, the M floats are all-reduced with MAX, and pq_act_quant_amax quantises the slice
+ * with that global maximum: codes and scales are then those of the unsharded quantizer.  pq_qgemm_i32_scatter
+ * multiplies the slices and stores the exact int32 partial sums of output columns [d*cols_per_dest,
+ * (d+1)*cols_per_dest) into dests[d] (row stride ld_dest elements) -- peer-mapped inboxes on the ranks that own
+ * those columns, written from the GEMM epilogue over NVLink in coalesced 256-byte segments.  After a barrier
+ * every owner runs pq_reduce_dequant over the n_parts inboxes: int32 addition is associative, so
+ *   y[m,n] = cast(((float(sum_p part_p[m,n]) * s_x[m]) * s_w[n]) + bias[n])
+ * is bit-identical to the unsharded pq_qgemm for any number of shards.  ys[0..n_ys) may again be peer-mapped
+ * (the all-gather of the finished slices fused into the same kernel).  With n_parts == 1 and n_ys == 1 this is
+ * simply the dequant epilogue applied to pq_qgemm_i32's accumulators. */
+int pq_row_absmax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, float* amax, void* stream);
+int pq_act_quant_amax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, const float* amax,
+                      int8_t* xq, int64_t ldq, float* s_x, const pq_quant_spec* spec, void* stream);
+int pq_qgemm_i32_scatter(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
+                         void* const* dests, int n_dests, int64_t ld_dest, int64_t cols_per_dest,
+                         int64_t M, int64_t N, int64_t K, void* stream);
+int pq_reduce_dequant(const int32_t* const* parts, int n_parts, int64_t ld_part,
+                      const float* s_x, const float* s_w, const float* bias,
+                      void* const* ys, int n_ys, int y_dtype, int64_t ldy,
+                      int64_t M, int64_t N, void* stream);
+
 /* Host-buffer convenience API (what bench.py's "e2e" number goes through).
  * A pq_linear owns device copies of (Wq, s_w, bias), a device activation/output
  * workspace for up to max_tokens rows, and a private stream. */

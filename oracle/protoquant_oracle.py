@@ -70,9 +70,13 @@ def to_f32(x) -> np.ndarray:
     raise TypeError(f"unsupported input dtype {x.dtype}")
 
 
-def rowwise_scale(x32: np.ndarray, spec: QuantSpec = SPEC_V0) -> Tuple[np.ndarray, np.ndarray]:
-    """(amax_eff, scale) per row of a [R, C] float32 matrix."""
-    amax = np.max(np.abs(x32), axis=-1).astype(np.float32) if x32.shape[-1] else np.zeros(x32.shape[:-1], np.float32)
+def rowwise_scale(x32: np.ndarray, spec: QuantSpec = SPEC_V0, amax: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """(amax_eff, scale) per row of a [R, C] float32 matrix.  `amax` overrides the row maxima (a K-shard of a
+    row-parallel layer quantises its slice with the maximum of the whole row)."""
+    if amax is not None:
+        amax = np.asarray(amax, dtype=np.float32)
+    else:
+        amax = np.max(np.abs(x32), axis=-1).astype(np.float32) if x32.shape[-1] else np.zeros(x32.shape[:-1], np.float32)
     if spec.eps > 0:
         amax = np.maximum(amax, np.float32(spec.eps))
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -81,14 +85,14 @@ def rowwise_scale(x32: np.ndarray, spec: QuantSpec = SPEC_V0) -> Tuple[np.ndarra
     return amax, s
 
 
-def quantize_rowwise(x, spec: QuantSpec = SPEC_V0) -> Tuple[np.ndarray, np.ndarray]:
+def quantize_rowwise(x, spec: QuantSpec = SPEC_V0, amax: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
     """Per-row symmetric int8 quantisation of a 2-D matrix.  Returns (q int8 [R,C], s fp32 [R]).
 
     Used both for activations (rows = tokens) and for weights
     W[N,K] (rows = output channels, row a2)."""
     x32 = to_f32(x)
     assert x32.ndim == 2
-    amax, s = rowwise_scale(x32, spec)
+    amax, s = rowwise_scale(x32, spec, amax)
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         if spec.scale_mode == DIV:
             r = (x32 / s[:, None]).astype(np.float32)

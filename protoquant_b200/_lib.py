@@ -23,6 +23,7 @@ EXPORTS = (
     "pq_qgemm", "pq_qgemm_multi", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
     "pq_linear_create", "pq_linear_forward_host", "pq_linear_destroy",
     "pq_norm_quant", "pq_act_mul_quant",
+    "pq_row_absmax", "pq_act_quant_amax", "pq_qgemm_i32_scatter", "pq_reduce_dequant",
 )
 
 
@@ -70,6 +71,14 @@ def _declare(lib):
     lib.pq_linear_destroy.argtypes = [vp]
     lib.pq_norm_quant.restype = i32
     lib.pq_norm_quant.argtypes = [vp, i32, i64, i64, i64, vp, vp, c.c_float, vp, i64, vp, vp, i64, specp, vp]
+    lib.pq_row_absmax.restype = i32
+    lib.pq_row_absmax.argtypes = [vp, i32, i64, i64, i64, vp, vp]
+    lib.pq_act_quant_amax.restype = i32
+    lib.pq_act_quant_amax.argtypes = [vp, i32, i64, i64, i64, vp, vp, i64, vp, specp, vp]
+    lib.pq_qgemm_i32_scatter.restype = i32
+    lib.pq_qgemm_i32_scatter.argtypes = [vp, i64, vp, i64, c.POINTER(vp), i32, i64, i64, i64, i64, i64, vp]
+    lib.pq_reduce_dequant.restype = i32
+    lib.pq_reduce_dequant.argtypes = [c.POINTER(vp), i32, i64, vp, vp, vp, c.POINTER(vp), i32, i32, i64, i64, i64, vp]
     lib.pq_act_mul_quant.restype = i32
     lib.pq_act_mul_quant.argtypes = [vp, vp, i32, i32, i64, i64, i64, i64, vp, i64, vp, vp, i64, specp, vp]
     if hasattr(lib, "pq_debug_set_quant_config"):

@@ -57,6 +57,9 @@ struct GemmArgs {
   int prefetch_b;           // 1 = warp 3 prefetches this CTA's weight boxes into L2 ahead of the ring
   int tma_store;            // staged epilogue hands its tiles to TMA bulk stores (single destination)
   int dbg;                  // profiling only (pq_debug_set_epilogue): bit 0 = the epilogue skips its global stores
+  int scatter_cols;         // > 0 (staged epilogue): columns [d*scatter_cols, (d+1)*scatter_cols) go to out[d] ONLY, as a
+                            // [M, scatter_cols] matrix with row stride ldo (fused GEMM + reduce-scatter: out[d] is this
+                            // rank's inbox on the rank that owns those output columns)
 };
 
 // WS_BYTES: per-warp TMA-store staging of the direct epilogue (16-bit outputs): every epilogue warp owns
@@ -185,7 +188,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
              const __grid_constant__ CUtensorMap tmap_y, const GemmArgs g) {
   using L = SmemLayout<CG, BN, STAGES, STAGED, (int)sizeof(OutT)>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
-  static_assert(!(STAGED && RAW), "staged epilogue is for typed outputs only");
   static_assert(!STAGED || BN == 256, "staged epilogue assumes 128-column halves");
   static_assert(MC == 1 || (MC == 2 && CG == 2 && (BN / 4) % 8 == 0), "multicast clusters are pairs of CTA pairs");
   constexpr int SUPER_M = BLOCK_M * CG * MC;   // rows of one scheduled tile (all CTAs of the cluster)
@@ -501,26 +503,31 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t r[32];
             tmem_ld_32x32(taddr0 + c * 32, r);
             tmem_ld_wait();
-            const float* sw = sw_smem + as * BNP + c * 32;
-            const float* bs = bias_smem + as * BNP + c * 32;
-            float f[32];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(sw + 4 * j4);
-              const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j4);
-              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-              const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float v = __int2float_rn((int)r[4 * j4 + j]);
-                v = __fmul_rn(v, sx);
-                v = __fmul_rn(v, wv[j]);
-                if (has_bias) v = __fadd_rn(v, bv[j]);
-                f[4 * j4 + j] = v;
-              }
-            }
             uint32_t o[OutPack<OT>::WORDS];
-            OutPack<OT>::pack(f, o);
+            if constexpr (RAW) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = r[j];     // exact int32 partial sums
+            } else {
+              const float* sw = sw_smem + as * BNP + c * 32;
+              const float* bs = bias_smem + as * BNP + c * 32;
+              float f[32];
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(sw + 4 * j4);
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j4);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float v = __int2float_rn((int)r[4 * j4 + j]);
+                  v = __fmul_rn(v, sx);
+                  v = __fmul_rn(v, wv[j]);
+                  if (has_bias) v = __fadd_rn(v, bv[j]);
+                  f[4 * j4 + j] = v;
+                }
+              }
+              OutPack<OT>::pack(f, o);
+            }
 #pragma unroll
             for (int i = 0; i < UPC; ++i) {
               const int u = cc * UPC + i;                          // unit inside the 256-byte pass row
@@ -556,7 +563,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const int gcol = colp + u * EPU;
               if (grow < g.M && gcol < g.N) {
                 const uint4 v = *reinterpret_cast<const uint4*>(stg + (u >> 3) * SUB + rr * 128 + (((u & 7) ^ (rr & 7)) << 4));
-                if (g.vec_ok && gcol + EPU <= g.N) {
+                if (g.scatter_cols > 0) {
+                  // reduce-scatter: this 16-byte unit belongs to exactly one destination (scatter_cols % EPU == 0)
+                  const int d = gcol / g.scatter_cols;
+                  OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + (gcol - d * g.scatter_cols);
+                  if (g.vec_ok && gcol + EPU <= g.N) {
+                    *reinterpret_cast<uint4*>(dst) = v;
+                  } else {
+                    const OT* ev = reinterpret_cast<const OT*>(&v);
+#pragma unroll
+                    for (int e = 0; e < EPU; ++e)
+                      if (gcol + e < g.N) dst[e] = ev[e];
+                  }
+                } else if (g.vec_ok && gcol + EPU <= g.N) {
                   for (int d = 0; d < g.n_out; ++d)
                     *reinterpret_cast<uint4*>(reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol) = v;
                 } else {
@@ -941,12 +960,10 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
   //   cfg 0: 1-CTA 128x256   cfg 1: 2-CTA 256x256   cfg 2: 1-CTA 128x128   cfg 3: 1-CTA 128x64
   //   cfg 16: 4-CTA multicast cluster, 512x256 super-tiles (experiment: no faster, see README_r1.md)
   //   cfg 4: 2-CTA 256x128   cfg 8/9/10: 2-CTA 256x{240,224,208}   cfg 11/12/13: 1-CTA 128x{240,224,208}
-  if constexpr (!std::is_same<OutT, int32_t>::value) {
-    if (g.n_out > 1 || g_force_staged) {
-      // fused all-gather: coalesced (shared-memory staged) stores to every destination
-      if (g.M > 128) return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
-      return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
-    }
+  if (g.n_out > 1 || g.scatter_cols > 0 || (g_force_staged && !std::is_same<OutT, int32_t>::value)) {
+    // fused all-gather / reduce-scatter: coalesced (shared-memory staged) stores to the peer destinations
+    if (g.M > 128) return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+    return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
   }
   int cfg = g_force_cfg;
   if (cfg < 0) {
@@ -1022,7 +1039,7 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,
                  void* const* outs, int n_out, int out_dtype, int64_t ldo,
-                 int64_t M, int64_t N, int64_t K, cudaStream_t stream) {
+                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols) {
   if (M < 0 || N < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "qgemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   if (M == 0 || N == 0) return PQ_OK;
   if (M > 0x7fffff00LL || N > 0x7fffff00LL || K > 0x7fffff00LL) PQ_FAIL(PQ_ERR_ARG, "qgemm: dimension too large");
@@ -1030,7 +1047,11 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   for (int d = 0; d < n_out; ++d)
     if (!outs[d]) PQ_FAIL(PQ_ERR_ARG, "qgemm: null destination %d", d);
   if (out_dtype != PQ_I32 && (!s_x || !s_w)) PQ_FAIL(PQ_ERR_ARG, "qgemm: null scale pointer");
-  if (lda < K || ldb < K || ldo < N) PQ_FAIL(PQ_ERR_ARG, "qgemm: leading dimension too small");
+  if (scatter_cols > 0) {
+    if (scatter_cols % 4 != 0 || scatter_cols * n_out < N || ldo < scatter_cols)
+      PQ_FAIL(PQ_ERR_ARG, "qgemm: scatter needs scatter_cols %% 4 == 0, n_out * scatter_cols >= N and ldo >= scatter_cols");
+  } else if (ldo < N) PQ_FAIL(PQ_ERR_ARG, "qgemm: leading dimension too small");
+  if (lda < K || ldb < K) PQ_FAIL(PQ_ERR_ARG, "qgemm: leading dimension too small");
   if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || (lda & 15) || (ldb & 15))
     PQ_FAIL(PQ_ERR_ALIGN, "qgemm: xq/Wq base pointers and row strides must be multiples of 16 bytes (TMA)");
   int num_sms = 0;
@@ -1040,7 +1061,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   // ... unless K is short: the cluster split-K machinery then costs more than it saves (64 x 4096 x 1024:
   // 11.4 us vs 5.0 us with 128x64 tiles; 64 x 4096 x 2048: 9.2 vs 6.4 us; 48 x 4096 x 4096: 8.3 vs 9.4 us).
   const bool smallm_pays = !(M > 32 && K <= 2048);
-  if (M <= 64 && n_out == 1 && !g_force_staged && g_sk_mode != 1 && ((g_force_cfg < 0 && smallm_pays) || g_force_cfg == 7))
+  if (M <= 64 && n_out == 1 && scatter_cols == 0 && !g_force_staged && g_sk_mode != 1 && ((g_force_cfg < 0 && smallm_pays) || g_force_cfg == 7))
     return launch_qgemm_smallm(a, lda, b, ldb, s_x, s_w, bias, outs[0], out_dtype, ldo, M, N, K, num_sms, stream);
   if (g_force_cfg == 7) PQ_FAIL(PQ_ERR_ARG, "qgemm: config 7 (small-M kernel) needs M <= 64");
   GemmArgs g = {};
@@ -1057,6 +1078,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   g.tl = g_timeline;
   g.prefetch_b = g_prefetch_b;
   g.dbg = g_epi_dbg;
+  g.scatter_cols = (int)scatter_cols;
   switch (out_dtype) {
     case PQ_BF16: return launch_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
     case PQ_F16: return launch_typed<__half>(a, lda, b, ldb, g, num_sms, stream);

@@ -53,7 +53,8 @@ template <typename T, int TPR, int VPT>
 __global__ void __launch_bounds__((TPR > 256 ? TPR : 256))
 rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t ldx,
                          int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
-                         int scale_mode, float eps, const uint8_t* __restrict__ pf, long long pf_bytes) {
+                         int scale_mode, float eps, const uint8_t* __restrict__ pf, long long pf_bytes,
+                         const float* __restrict__ amax_in) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
@@ -109,6 +110,8 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
 #pragma unroll
     for (int w = 0; w < WPR; ++w) amax = fmaxf(amax, red[row_in_cta][w]);
   }
+  // row-parallel shards quantise a K-slice with the |.|-max of the WHOLE row (pq_act_quant_amax)
+  if (amax_in != nullptr && row_ok) amax = __ldg(amax_in + row);
 
   const RowQ rq = make_rowq(amax, scale_mode, eps);
   if (row_ok && t == 0) s_out[row] = rq.s;
@@ -151,7 +154,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int64_t ldx,
                              int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
-                             int transpose, int scale_mode, float eps) {
+                             int transpose, int scale_mode, float eps, const float* __restrict__ amax_in) {
   __shared__ float red[8];
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
@@ -165,6 +168,7 @@ rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int6
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < 8; ++w) amax = fmaxf(amax, red[w]);
+  if (amax_in != nullptr) amax = __ldg(amax_in + row);
   const RowQ rq = make_rowq(amax, scale_mode, eps);
   if (threadIdx.x == 0) s_out[row] = rq.s;
   for (int64_t k = threadIdx.x; k < K; k += 256) {
@@ -286,13 +290,14 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
 
 template <typename T, int TPR, int VPT>
 int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int64_t ldq,
-               float* s, const pq_quant_spec& spec, cudaStream_t st, const void* pf, long long pf_bytes) {
+               float* s, const pq_quant_spec& spec, cudaStream_t st, const void* pf, long long pf_bytes,
+               const float* amax_in) {
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
   const int64_t grid = (M + ROWS - 1) / ROWS;
   PQ_CUDA(launch_pdl(rowwise_quant_vec_kernel<T, TPR, VPT>, (unsigned)grid, THREADS, st,
                      (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps,
-                     (const uint8_t*)pf, pf_bytes));
+                     (const uint8_t*)pf, pf_bytes, amax_in));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;
 }
@@ -300,11 +305,12 @@ int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int6
 template <typename T>
 int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq,
              float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st,
-             const void* pf, long long pf_bytes) {
+             const void* pf, long long pf_bytes, const float* amax_in) {
   constexpr int EPV = VecTraits<T>::EPV;
   if (M == 0) return PQ_OK;
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
   if (transpose) {
+    if (amax_in) PQ_FAIL(PQ_ERR_UNSUPPORTED, "rowwise quant: an external row maximum cannot be combined with transpose");
     const int64_t grid = (M + 31) / 32;
     const bool tvec = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) && ((ldx * (int64_t)sizeof(T)) % 16 == 0) &&
                       (((uintptr_t)xq & 15) == 0) && (ldq % 16 == 0);
@@ -323,7 +329,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
                       (K / EPV <= 8192);
   if (!vec_ok) {
     PQ_CUDA(launch_pdl(rowwise_quant_generic_kernel<T>, (unsigned)M, 256u, st,
-                       (const T*)x, M, K, ldx, xq, ldq, s, 0, spec.scale_mode, spec.eps));
+                       (const T*)x, M, K, ldx, xq, ldq, s, 0, spec.scale_mode, spec.eps, amax_in));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return PQ_OK;
   }
@@ -349,7 +355,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
     if (score < best_score) { best_score = score; best_tpr = tpr; best_vpt = vpt; }
   }
   if (g_force_tpr > 0 && g_force_vpt > 0 && g_force_tpr * g_force_vpt >= nvec) { best_tpr = g_force_tpr; best_vpt = g_force_vpt; }
-#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes);
+#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes, amax_in);
 #define PQ_CASE_T(TPR) PQ_CASE_V(TPR, 2) PQ_CASE_V(TPR, 3) PQ_CASE_V(TPR, 4) PQ_CASE_V(TPR, 6) PQ_CASE_V(TPR, 8)
   PQ_CASE_T(32) PQ_CASE_T(64) PQ_CASE_T(128) PQ_CASE_T(256) PQ_CASE_T(512) PQ_CASE_T(1024)
 #undef PQ_CASE_T
@@ -362,7 +368,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
 int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
                          int8_t* xq, int64_t ldq, float* s, int transpose,
                          const pq_quant_spec& spec, cudaStream_t stream,
-                         const void* prefetch, long long prefetch_bytes) {
+                         const void* prefetch, long long prefetch_bytes, const float* amax_in) {
   if (((uintptr_t)prefetch & 15) || prefetch_bytes < 16 || !g_weight_prefetch) { prefetch = nullptr; prefetch_bytes = 0; }
   if (M < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: bad shape M=%lld K=%lld", (long long)M, (long long)K);
   if (M > 0 && (!x || !xq || !s)) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: null pointer");
@@ -374,9 +380,9 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
   if (spec.qmin != -128 && spec.qmin != -127)
     PQ_FAIL(PQ_ERR_ARG, "rowwise quant: qmin must be -128 or -127");
   switch (x_dtype) {
-    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes);
-    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes);
-    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes);
+    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in);
+    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in);
+    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in);
     default: PQ_FAIL(PQ_ERR_ARG, "rowwise quant: unsupported dtype %d", x_dtype);
   }
 }

@@ -206,6 +206,73 @@ def qlinear_into(x2: torch.Tensor, wq_storage: torch.Tensor, in_features: int, s
     return y
 
 
+def row_absmax(x: torch.Tensor) -> torch.Tensor:
+    """amax[m] = max_k |x[m,k]| in fp32 (the per-token statistic a K-sharded quantizer all-reduces)."""
+    _require_cuda(x, "x")
+    x2 = _rows2d(x) if x.dim() == 2 and x.stride(1) == 1 else x.reshape(-1, x.shape[-1]).contiguous()
+    M, K = x2.shape
+    amax = torch.empty((M,), dtype=torch.float32, device=x.device)
+    if M:
+        _lib.check(_lib.lib().pq_row_absmax(x2.data_ptr(), _DT[x2.dtype], M, K, x2.stride(0), amax.data_ptr(), _stream()),
+                   "pq_row_absmax")
+    return amax
+
+
+def quantize_act_with_amax(x: torch.Tensor, amax: torch.Tensor, spec: Optional[QuantSpec] = None):
+    """Quantise x [M,Ks] (a K-slice of the activation) with the given per-row maxima of the WHOLE row."""
+    _require_cuda(x, "x")
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.reshape(-1, x.shape[-1]).contiguous()
+    M, K = x.shape
+    if amax.dtype != torch.float32 or amax.numel() != M or not amax.is_contiguous():
+        raise TypeError("amax must be a contiguous fp32 tensor with one entry per row")
+    xq = alloc_q(M, K, x.device)
+    s_x = torch.empty((M,), dtype=torch.float32, device=x.device)
+    if M:
+        _lib.check(_lib.lib().pq_act_quant_amax(x.data_ptr(), _DT[x.dtype], M, K, x.stride(0), amax.data_ptr(),
+                                                xq.data_ptr(), xq.stride(0), s_x.data_ptr(), _specp(spec), _stream()),
+                   "pq_act_quant_amax")
+    return xq, s_x
+
+
+def qgemm_i32_scatter(xq: torch.Tensor, wq: torch.Tensor, dest_ptrs, ld_dest: int, cols_per_dest: int) -> None:
+    """int32 GEMM whose output columns [d*cols_per_dest, (d+1)*cols_per_dest) are stored to the raw device
+    address dest_ptrs[d] as an [M, cols_per_dest] int32 matrix (row stride ld_dest): the GEMM half of the fused
+    GEMM + reduce-scatter (dest_ptrs are peer-mapped inboxes)."""
+    xq = _gemm_operand(xq, "xq")
+    wq = _gemm_operand(wq, "wq")
+    M, K = xq.shape
+    N = wq.shape[0]
+    arr = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
+    if M and N:
+        _lib.check(_lib.lib().pq_qgemm_i32_scatter(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), arr,
+                                                   len(dest_ptrs), ld_dest, cols_per_dest, M, N, K, _stream()),
+                   "pq_qgemm_i32_scatter")
+
+
+def reduce_dequant(part_ptrs, ld_part: int, s_x: torch.Tensor, s_w: torch.Tensor, bias: Optional[torch.Tensor],
+                   dest_ptrs, ldy: int, out_dtype: torch.dtype, M: int, N: int) -> None:
+    """y = cast(((float(sum of the int32 parts) * s_x[m]) * s_w[n]) + bias[n]) written to every dest_ptrs[d]."""
+    pa = (ctypes.c_void_p * len(part_ptrs))(*[ctypes.c_void_p(int(p)) for p in part_ptrs])
+    da = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
+    if M and N:
+        _lib.check(_lib.lib().pq_reduce_dequant(pa, len(part_ptrs), ld_part, s_x.data_ptr(), s_w.data_ptr(),
+                                                bias.data_ptr() if bias is not None else None, da, len(dest_ptrs),
+                                                _DT[out_dtype], ldy, M, N, _stream()), "pq_reduce_dequant")
+
+
+def dequant_accumulators(acc: torch.Tensor, s_x: torch.Tensor, s_w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """The fused epilogue as a stand-alone op on int32 accumulators acc [M,N] (e.g. after an exact all-reduce)."""
+    _require_cuda(acc, "acc")
+    if acc.dtype != torch.int32 or acc.dim() != 2 or acc.stride(1) != 1:
+        raise TypeError("acc must be a 2-D int32 tensor with unit column stride")
+    M, N = acc.shape
+    y = torch.empty((M, N), dtype=out_dtype, device=acc.device)
+    reduce_dequant([acc.data_ptr()], acc.stride(0), s_x, s_w, bias, [y.data_ptr()], N, out_dtype, M, N)
+    return y
+
+
 _ACTS = {"identity": _lib.PQ_ACT_IDENTITY, "silu": _lib.PQ_ACT_SILU, "gelu": _lib.PQ_ACT_GELU,
          "gelu_tanh": _lib.PQ_ACT_GELU_TANH}
 

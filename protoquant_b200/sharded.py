@@ -149,6 +149,144 @@ class ShardedDynamicQuantLinear(nn.Module):
         return y.reshape(*lead, self.out_features)
 
 
+class _CudaShardOps:
+    """The device ops of the row-parallel module (tests on a CPU-only box inject oracle versions)."""
+    row_absmax = staticmethod(F.row_absmax)
+    quantize_with_amax = staticmethod(F.quantize_act_with_amax)
+    int_mm = staticmethod(F.qgemm_i32)
+    epilogue = staticmethod(F.dequant_accumulators)
+
+
+class RowParallelDynamicQuantLinear(nn.Module):
+    """Row-parallel (K-split) dynamic-quant linear: rank r holds columns [k_lo, k_hi) of Wq, so
+    a column-parallel up-projection can feed it without a gather in between (Megatron MLP layout).
+
+    * The per-token scale is the maximum over the WHOLE row: with `input_is_sharded` each rank takes the maximum
+      of its K-slice and the M floats are all-reduced with MAX; a replicated input needs no communication.
+      Every rank then quantises its slice with the global maximum, i.e. produces exactly the codes and scales of
+      the unsharded quantizer.
+    * The K-slices' int32 partial sums are exact and associative, so the reduce step is done on int32 and the
+      dequant epilogue runs once on the sum: the output is bit-identical to the 1-GPU module for any world size.
+    * Fused exchange (CUDA + symmetric memory): the GEMM epilogue stores each output-column block straight into
+      the inbox of the rank that owns it (NVLink peer stores, `pq_qgemm_i32_scatter`); after one barrier the
+      owner sums its `world` inboxes, applies scales and bias and -- with `gather_output` -- writes the finished
+      slice into every rank's output buffer (`pq_reduce_dequant`): GEMM + reduce-scatter + all-gather in two
+      kernels and two barriers, no NCCL call on the data path.
+    * Fallback (gloo, or no symmetric memory): int32 all-reduce(SUM) of the partial sums + local epilogue.
+    """
+
+    def __init__(self, qweight_full: torch.Tensor, weight_scale_full: torch.Tensor,
+                 bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,
+                 spec: Optional[F.QuantSpec] = None, input_is_sharded: bool = False, gather_output: bool = True,
+                 ops=None, fused: Optional[bool] = None):
+        super().__init__()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.out_features, self.in_features = qweight_full.shape
+        self.out_dtype = out_dtype
+        self.spec = spec
+        self.input_is_sharded = input_is_sharded
+        self.gather_output = gather_output
+        self.ops = ops or _CudaShardOps
+        self.fused = fused
+        self._symm = None
+        self._flip = 0
+        self.k_lo, self.k_hi = shard_bounds(self.in_features, self.world, self.rank, align=16)
+        if self.k_hi <= self.k_lo:
+            raise ValueError(f"in_features={self.in_features} is too small to split over {self.world} ranks")
+        self.per_n = shard_bounds(self.out_features, self.world, 0, align=8)[1]
+        self.n_lo, self.n_hi = shard_bounds(self.out_features, self.world, self.rank, align=8)
+        dev = qweight_full.device
+        ks = self.k_hi - self.k_lo
+        wq = torch.zeros((self.out_features, (ks + 15) // 16 * 16), dtype=torch.int8, device=dev)
+        wq[:, :ks].copy_(qweight_full[:, self.k_lo:self.k_hi])
+        self.register_buffer("qweight_storage", wq)
+        self.register_buffer("weight_scale", weight_scale_full.to(torch.float32).clone())
+        if bias_full is not None:
+            self.register_buffer("bias", bias_full.to(torch.float32).clone())
+        else:
+            self.bias = None
+
+    @property
+    def qweight(self):
+        return self.qweight_storage[:, : self.k_hi - self.k_lo]
+
+    def _quantize(self, x2: torch.Tensor):
+        amax = self.ops.row_absmax(x2)
+        if self.input_is_sharded and self.world > 1:
+            dist.all_reduce(amax, op=dist.ReduceOp.MAX, group=self.group)
+        xs = x2 if self.input_is_sharded else x2[:, self.k_lo:self.k_hi]
+        return self.ops.quantize_with_amax(xs, amax, self.spec)
+
+    def _symm_buffers(self, rows: int, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (dtype,)
+        if self._symm is not None and self._symm[0] == key and self._symm[1] >= rows:
+            return self._symm[1], self._symm[2]
+        cap = max(rows, 16)
+        group = self.group if self.group is not None else dist.group.WORLD
+        bufs = []
+        for _ in range(2):
+            inbox = symm_mem.empty((self.world, cap, self.per_n), dtype=torch.int32, device=device)
+            hi = symm_mem.rendezvous(inbox, group)
+            out = symm_mem.empty((cap, self.world * self.per_n), dtype=dtype, device=device)
+            ho = symm_mem.rendezvous(out, group)
+            bufs.append((inbox, hi, out, ho))
+        self._symm = (key, cap, bufs)
+        return cap, bufs
+
+    def _forward_fused(self, xq, s_x, M: int, out_dtype) -> torch.Tensor:
+        cap, bufs = self._symm_buffers(M, out_dtype, xq.device)
+        inbox, hi, out, ho = bufs[self._flip]
+        self._flip ^= 1
+        slot = cap * self.per_n * 4                      # bytes of one source rank's inbox
+        F.qgemm_i32_scatter(xq, self.qweight, [int(p) + self.rank * slot for p in hi.buffer_ptrs],
+                            self.per_n, self.per_n)
+        hi.barrier()                                     # every rank's partial sums have landed
+        n_mine = self.n_hi - self.n_lo
+        parts = [inbox.data_ptr() + s * slot for s in range(self.world)]
+        sw = self.weight_scale[self.n_lo:self.n_hi]
+        b = self.bias[self.n_lo:self.n_hi] if self.bias is not None else None
+        if not self.gather_output:
+            y = torch.empty((M, n_mine), dtype=out_dtype, device=xq.device)
+            if n_mine:
+                F.reduce_dequant(parts, self.per_n, s_x, sw, b, [y.data_ptr()], n_mine, out_dtype, M, n_mine)
+            return y
+        esz = out.element_size()
+        if n_mine:
+            F.reduce_dequant(parts, self.per_n, s_x, sw, b, [int(p) + self.n_lo * esz for p in ho.buffer_ptrs],
+                             self.world * self.per_n, out_dtype, M, n_mine)
+        ho.barrier()
+        return out[:M, : self.out_features]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        out_dtype = self.out_dtype or x.dtype
+        xq, s_x = self._quantize(x2)
+        M = x2.shape[0]
+        n_out = self.out_features if (self.gather_output or self.world == 1) else self.n_hi - self.n_lo
+        if self.world > 1 and self.ops is _CudaShardOps and x2.is_cuda and self.fused is not False:
+            try:
+                y = self._forward_fused(xq, s_x, M, out_dtype)
+                self.fused = True
+                return y.reshape(*lead, n_out)
+            except Exception:
+                if self.fused is True:
+                    raise
+                self.fused = False
+        acc = self.ops.int_mm(xq, self.qweight)              # exact int32 partial sums of this K-slice
+        if self.world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        if self.gather_output or self.world == 1:
+            y = self.ops.epilogue(acc, s_x, self.weight_scale, self.bias, out_dtype)
+        else:
+            y = self.ops.epilogue(acc[:, self.n_lo:self.n_hi].contiguous(), s_x, self.weight_scale[self.n_lo:self.n_hi],
+                                  self.bias[self.n_lo:self.n_hi] if self.bias is not None else None, out_dtype)
+        return y.reshape(*lead, n_out)
+
+
 def maybe_shard(linear_q, group=None, min_out_features: int = 16384, **kw):
     """Shard a DynamicQuantLinear across `group` only if it is big enough to benefit."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1 or linear_q.out_features < min_out_features:

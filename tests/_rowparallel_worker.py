@@ -1,0 +1,78 @@
+"""torchrun worker for test_row_parallel_module_nvlink_bit_identical: the K-split module (fused GEMM +
+reduce-scatter + all-gather over symmetric memory, and the int32 all-reduce fallback) must be bit-identical to
+the single-GPU module on every rank; prints timings of the Llama-70B down projection."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import protoquant_b200 as pq  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    torch.manual_seed(0)
+    ok = True
+    for (N, K, M) in ((8192, 28672, 256), (4096, 11008, 2048), (1000, 512, 33), (8192, 28672, 16)):
+        lin = torch.nn.Linear(K, N).to(torch.bfloat16).cuda()
+        m = pq.DynamicQuantLinear.from_float(lin)
+        x = torch.randn(M, K, dtype=torch.bfloat16, device="cuda")
+        x[0, K - 1] = 25.0
+        full = m(x)
+        for fused in (False, True):
+            for sharded_in in (False, True):
+                for gather in (True, False):
+                    rp = pq.RowParallelDynamicQuantLinear(m.qweight, m.weight_scale, m.bias, fused=fused,
+                                                          input_is_sharded=sharded_in, gather_output=gather)
+                    xin = x[:, rp.k_lo:rp.k_hi].contiguous() if sharded_in else x
+                    want = full if gather else full[:, rp.n_lo:rp.n_hi]
+                    for _ in range(3):                      # repeated forwards exercise the double buffering
+                        y = rp(xin)
+                        same = torch.equal(y, want)
+                        ok = ok and same
+                        if not same:
+                            print(f"rank {rank} MISMATCH N={N} K={K} M={M} fused={fused} sharded_in={sharded_in} gather={gather}")
+            if rank == 0:
+                print(f"N={N} K={K} M={M} fused={fused} -> {rp.fused}")
+    # timing: Llama-70B down projection 28672 -> 8192 at 2048 tokens
+    N, K, M = 8192, 28672, 2048
+    lin = torch.nn.Linear(K, N, bias=False).to(torch.bfloat16).cuda()
+    m = pq.DynamicQuantLinear.from_float(lin)
+    x = torch.randn(M, K, dtype=torch.bfloat16, device="cuda")
+    mods = {"replicated": m,
+            "row_parallel_int32_allreduce": pq.RowParallelDynamicQuantLinear(m.qweight, m.weight_scale, None, fused=False),
+            "row_parallel_fused": pq.RowParallelDynamicQuantLinear(m.qweight, m.weight_scale, None, fused=True),
+            "row_parallel_fused_sharded_in_scattered_out": pq.RowParallelDynamicQuantLinear(
+                m.qweight, m.weight_scale, None, fused=True, input_is_sharded=True, gather_output=False)}
+    for name, mod in mods.items():
+        xin = x[:, mod.k_lo:mod.k_hi].contiguous() if getattr(mod, "input_is_sharded", False) else x
+        for _ in range(3):
+            mod(xin)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            mod(xin)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 20], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"TIMING down_proj 28672->8192 M=2048 world={dist.get_world_size()} {name}: {t.item()*1e3:.1f} us")
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("ROWPARALLEL_OK" if t.item() == 1 else "ROWPARALLEL_MISMATCH")
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

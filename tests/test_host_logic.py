@@ -113,6 +113,69 @@ def test_column_parallel_gloo_world2_bit_identical(N):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+class _OracleShardOps:
+    """CPU stand-ins for the device ops of RowParallelDynamicQuantLinear (oracle arithmetic)."""
+    @staticmethod
+    def row_absmax(x2):
+        return torch.from_numpy(np.max(np.abs(O.to_f32(x2)), axis=-1).astype(np.float32))
+
+    @staticmethod
+    def quantize_with_amax(xs, amax, spec=None):
+        q, s = O.quantize_rowwise(xs, amax=amax.numpy())
+        return torch.from_numpy(q), torch.from_numpy(s)
+
+    @staticmethod
+    def int_mm(xq, wq):
+        return torch.from_numpy(O.int_mm(xq.numpy(), wq.numpy()))
+
+    @staticmethod
+    def epilogue(acc, s_x, s_w, bias, out_dtype):
+        name = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[out_dtype]
+        return O.cast_out(O.dequant_epilogue(acc.numpy(), s_x.numpy(), s_w.numpy(), None if bias is None else bias.numpy()), name)
+
+
+def _row_worker(rank, world, port, N, K, M, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        w = (torch.rand(N, K) * 2 - 1) / K ** 0.5
+        b = torch.randn(N)
+        x = torch.randn(M, K).to(torch.bfloat16)
+        x[0, K - 1] = 40.0            # the row maximum lives in the LAST shard: local maxima would differ
+        wq, sw = O.quantize_rowwise(w)
+        full = O.qlinear(x, wq, sw, b.numpy(), out_dtype="bf16")
+        ok = True
+        for sharded_in in (False, True):
+            for gather in (True, False):
+                lin = pq.RowParallelDynamicQuantLinear(torch.from_numpy(wq), torch.from_numpy(sw), b, ops=_OracleShardOps,
+                                                       input_is_sharded=sharded_in, gather_output=gather)
+                xin = x[:, lin.k_lo:lin.k_hi].contiguous() if sharded_in else x
+                y = lin(xin)
+                want = full if gather else full[:, lin.n_lo:lin.n_hi]
+                ok = ok and torch.equal(y, want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,K", [(64, 96), (100, 200)])
+def test_row_parallel_gloo_world2_bit_identical(N, K):
+    """K-split shards + int32 all-reduce: same bits as the unsharded oracle, whether the input arrives replicated
+    or already K-sharded (max all-reduce), gathered or scattered output."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_row_worker, args=(r, 2, port, N, K, 6, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_maybe_shard_keeps_small_layers_replicated():
     m = pq.DynamicQuantLinear(64, 32)
     assert pq.maybe_shard(m) is m
