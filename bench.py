@@ -469,6 +469,12 @@ def run_ours(args):
             fused["llama7b_block_fused_2048tok"] = fused_block_leg(F, torch, dev, mods, acts)
         except Exception as ex:
             fused = {"error": repr(ex)[:200]}
+    bert = None
+    if rank == 0:
+        try:
+            bert = bert_leg(pq, F, torch, dev)
+        except Exception as ex:
+            bert = {"error": repr(ex)[:200]}
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1) else None
     clocks = sampler.result()
     if rank == 0:
@@ -483,7 +489,7 @@ def run_ours(args):
             "tokens_per_s": world * M_TOKENS / (ms_per_step * 1e-3),
             "frac_of_nominal_int8": value / world / NOMINAL_INT8_TOPS,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "sharded_70b": sharded, "decode_16tok": decode, "fused_producers": fused,
+            "clocks": clocks, "sharded_70b": sharded, "decode_16tok": decode, "fused_producers": fused, "bert_base_4096tok": bert,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -585,6 +591,94 @@ def fused_producer_leg(F, torch, dev, peaks):
     return res
 
 
+def bert_leg(pq, F, torch, dev):
+    """BASELINE.json configs[1]: the six linears of a BERT-base encoder layer (768 / 3072) at batch 32 x seq 128 =
+    4096 tokens, each as act-quant + GEMM (12 launches), and the same layer with LayerNorm -> int8 and GELU -> int8
+    fused into the producers (9 launches).  CUDA-graph replay."""
+    M = 32 * 128
+    shapes = [("q", 768, 768), ("k", 768, 768), ("v", 768, 768), ("o", 768, 768), ("ffn_up", 768, 3072), ("ffn_down", 3072, 768)]
+    ops = sum(2 * M * k * n for _, k, n in shapes)
+    mods = {}
+    for name, k, n in shapes:
+        m = pq.DynamicQuantLinear(k, n, bias=True, device=dev)
+        m.qweight_storage.random_(-127, 128)
+        m.weight_scale.uniform_(1e-4, 1e-3)
+        mods[name] = m
+    x = torch.randn(M, 768, device=dev).to(torch.bfloat16)
+    ctx = torch.randn(M, 768, device=dev).to(torch.bfloat16)
+    ln_w = torch.ones(768, dtype=torch.bfloat16, device=dev)
+    ln_b = torch.zeros(768, dtype=torch.bfloat16, device=dev)
+    outs = {name: torch.empty(M, n, dtype=torch.bfloat16, device=dev) for name, k, n in shapes}
+    ws768 = (F.alloc_q(M, 768, dev), torch.empty(M, dtype=torch.float32, device=dev))
+    ws3072 = (F.alloc_q(M, 3072, dev), torch.empty(M, dtype=torch.float32, device=dev))
+
+    def lin(name, inp, ws):
+        m = mods[name]
+        F.qlinear_into(inp, m.qweight_storage, m.in_features, m.weight_scale, m.bias, outs[name], *ws)
+
+    def gemm(name, ws):
+        m = mods[name]
+        F.qgemm(ws[0], ws[1], m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
+
+    def unfused():
+        for n in ("q", "k", "v"):
+            lin(n, x, ws768)
+        lin("o", ctx, ws768)
+        lin("ffn_up", outs["o"], ws768)
+        lin("ffn_down", outs["ffn_up"], ws3072)       # (GELU left out: it is not on the path)
+
+    def fused():
+        F.quantize_act(x, out=ws768)
+        for n in ("q", "k", "v"):
+            gemm(n, ws768)
+        F.quantize_act(ctx, out=ws768)
+        gemm("o", ws768)
+        F.layernorm_quant(outs["o"], ln_w, ln_b, out=ws768)        # attention-output LayerNorm -> int8
+        gemm("ffn_up", ws768)
+        F.act_mul_quant(outs["ffn_up"], None, act="gelu", out=ws3072)   # GELU -> int8
+        gemm("ffn_down", ws3072)
+
+    tmp768 = torch.empty(M, 768, dtype=torch.bfloat16, device=dev)
+    tmp3072 = torch.empty(M, 3072, dtype=torch.bfloat16, device=dev)
+
+    def unfused_with_ops():
+        # the same layer as `fused`, with torch's LayerNorm and GELU as separate kernels in front of the quantizers
+        for n in ("q", "k", "v"):
+            lin(n, x, ws768)
+        lin("o", ctx, ws768)
+        tmp768.copy_(torch.nn.functional.layer_norm(outs["o"], (768,), ln_w, ln_b, 1e-12))
+        lin("ffn_up", tmp768, ws768)
+        tmp3072.copy_(torch.nn.functional.gelu(outs["ffn_up"]))
+        lin("ffn_down", tmp3072, ws3072)
+
+    res = {"tokens": M, "linears": {n: [k, nn_] for n, k, nn_ in shapes},
+           "note": "act_quant_per_linear = the six linears alone (12 launches); with_torch_layernorm_gelu adds the two "
+                   "producer ops as torch kernels; fused_producers computes them inside the quantizing kernels (9 launches)"}
+    for label, fn in (("act_quant_per_linear", unfused), ("with_torch_layernorm_gelu", unfused_with_ops),
+                      ("fused_producers", fused)):
+        fn()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(3):
+            g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(50):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 50
+        res[label] = {"ms_per_layer": ms, "tops": ops / (ms * 1e-3) / 1e12, "tokens_per_s": M / (ms * 1e-3)}
+    return res
+
+
 def fused_block_leg(F, torch, dev, mods, acts):
     """The same seven GEMMs wired the way a Llama block uses them, with the producer fusions (§8f-2): RMSNorm -> int8
     once for q/k/v, once for gate/up; silu(gate)*up -> int8 straight from the gate/up outputs; 4 quantising launches
@@ -675,6 +769,36 @@ def sharded_leg(pq, torch, dist, dev, rank, world):
             res[f"M{M}_bit_identical"] = bool(torch.equal(sh(x), full(x)) and torch.equal(shf(x), full(x)))
     if shf is not None:
         res["fused_path_active"] = bool(shf.fused)
+    # row-parallel (K-split) down projection 28672 -> 8192: fused GEMM + reduce-scatter (+ all-gather) on int32 partials
+    if world > 1:
+        Kd, Nd = 28672, 8192
+        wq_d = torch.randint(-127, 128, (Nd, Kd), dtype=torch.int8, device=dev, generator=g)
+        sw_d = torch.rand(Nd, device=dev, generator=g) * 1e-3
+        full_d = pq.DynamicQuantLinear(Kd, Nd, bias=False, device=dev)
+        full_d.qweight_storage[:, :Kd].copy_(wq_d)
+        full_d.weight_scale.copy_(sw_d)
+        rp = pq.RowParallelDynamicQuantLinear(wq_d, sw_d, None, fused=None)
+        rps = pq.RowParallelDynamicQuantLinear(wq_d, sw_d, None, fused=None, input_is_sharded=True, gather_output=False)
+        x = torch.randn(2048, Kd, device=dev, generator=g).to(torch.bfloat16)
+        down = {"layer": [Kd, Nd], "M": 2048}
+        for label, mod, xin in (("replicated", full_d, x), ("row_parallel_fused", rp, x),
+                                ("row_parallel_fused_sharded_in_scattered_out", rps, x[:, rps.k_lo:rps.k_hi].contiguous())):
+            for _ in range(3):
+                mod(xin)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                y = mod(xin)
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            down[label] = {"ms": t.item(), "tops": 2 * 2048 * Nd * Kd / (t.item() * 1e-3) / 1e12}
+        down["bit_identical"] = bool(torch.equal(rp(x), full_d(x)))
+        down["fused_path_active"] = bool(rp.fused)
+        res["down_proj_row_parallel"] = down
     return res
 
 
