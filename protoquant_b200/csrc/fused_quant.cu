@@ -233,8 +233,15 @@ __device__ __forceinline__ void norm_quant_body(const NormArgs& a) {
         unpack<T>(__ldg(reinterpret_cast<const uint4*>(gr + (long long)vi * EPV)), g);
         unpack<T>(__ldg(reinterpret_cast<const uint4*>(br + (long long)vi * EPV)), b);
 #pragma unroll
-        for (int j = 0; j < EPV; ++j) f[j] = round_to<T>(fmaf(__fmul_rn(f[j] - mean, rstd), g[j], b[j]));
-        v[i] = pack_vec<T>(f);
+        for (int j = 0; j < EPV; ++j) f[j] = fmaf(__fmul_rn(f[j] - mean, rstd), g[j], b[j]);
+        if (sizeof(T) == 2) {        // one rounding to T, two elements per cvt
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = Pk<T>::cvt2(f[(2 * j) % EPV], f[(2 * j + 1) % EPV]);
+          v[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+          v[i] = pack_vec<T>(f);
+        }
       }
     }
   } else {
