@@ -8,7 +8,7 @@ from .functional import (DEFAULT_SPEC, QuantSpec, act_mul_quant, dequantize as d
                          norm_quant, qgemm, qgemm_i32, qlinear, quantize_act, quantize_weight, rmsnorm_quant)
 from .modules import DynamicQuantLinear, swap_linear
 from .qtensor import QTensor, dequantize, quantize
-from .sharded import RowParallelDynamicQuantLinear, ShardedDynamicQuantLinear, maybe_shard, shard_bounds
+from .sharded import ParallelGatedMLP, RowParallelDynamicQuantLinear, ShardedDynamicQuantLinear, maybe_shard, shard_bounds
 
 __version__ = "0.1.0"
 __all__ = [
@@ -16,5 +16,5 @@ __all__ = [
     "quantize_act", "quantize_weight", "qgemm", "qgemm_i32", "qlinear", "dequantize_tensor",
     "norm_quant", "rmsnorm_quant", "layernorm_quant", "act_mul_quant",
     "QTensor", "quantize", "dequantize", "DynamicQuantLinear", "swap_linear",
-    "ShardedDynamicQuantLinear", "RowParallelDynamicQuantLinear", "maybe_shard", "shard_bounds",
+    "ShardedDynamicQuantLinear", "RowParallelDynamicQuantLinear", "ParallelGatedMLP", "maybe_shard", "shard_bounds",
 ]

@@ -356,6 +356,12 @@ def act_mul_quant(gate: torch.Tensor, up: Optional[torch.Tensor] = None, act: st
     return (hq, s_h, h.reshape(gate.shape)) if return_float else (hq, s_h)
 
 
+def act_mul(gate: torch.Tensor, up: Optional[torch.Tensor] = None, act: str = "silu") -> torch.Tensor:
+    """T(T(act(gate)) * up) as a tensor of the input dtype: exactly the tensor `act_mul_quant` quantises (used where
+    the quantisation has to wait for a cross-rank row maximum)."""
+    return act_mul_quant(gate, up, act, return_float=True)[2]
+
+
 def dequantize(q: torch.Tensor, s: torch.Tensor, axis: int = 0, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """out[r,c] = q[r,c] * s[r] (axis=0) or q[r,c] * s[c] (axis=1)."""
     _require_cuda(q, "q")

@@ -44,7 +44,8 @@ class ShardedDynamicQuantLinear(nn.Module):
     def __init__(self, qweight_full: torch.Tensor, weight_scale_full: torch.Tensor,
                  bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,
                  spec: Optional[F.QuantSpec] = None,
-                 local_forward: Optional[Callable] = None, fused: Optional[bool] = None):
+                 local_forward: Optional[Callable] = None, fused: Optional[bool] = None,
+                 gather_output: bool = True, align: int = 8):
         """qweight_full [N,K] int8, weight_scale_full [N] fp32, bias_full [N] fp32|None: the
         UNSHARDED quantised weight (every rank passes the same tensors; each keeps its slice).
         `local_forward(x2d, wq, s_w, bias, out_dtype)` defaults to the CUDA path; tests on a
@@ -61,9 +62,11 @@ class ShardedDynamicQuantLinear(nn.Module):
         self.fused = fused
         self._symm = None      # (capacity_rows, dtype) -> [(tensor, handle), (tensor, handle)]
         self._flip = 0
-        per = shard_bounds(self.out_features, self.world, 0)[1]
+        # gather_output=False keeps the [tokens, hi-lo] slice local (it feeds a row-parallel layer, §8f-3)
+        self.gather_output = gather_output
+        per = shard_bounds(self.out_features, self.world, 0, align)[1]
         self.per = per
-        lo, hi = shard_bounds(self.out_features, self.world, self.rank)
+        lo, hi = shard_bounds(self.out_features, self.world, self.rank, align)
         self.lo, self.hi = lo, hi
         dev = qweight_full.device
         kp = (self.in_features + 15) // 16 * 16
@@ -130,6 +133,9 @@ class ShardedDynamicQuantLinear(nn.Module):
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         out_dtype = self.out_dtype or x.dtype
+        if not self.gather_output:
+            y_local = self.local(x2, out_dtype)
+            return y_local[:, : self.hi - self.lo].reshape(*lead, self.hi - self.lo)
         if self.world > 1 and self._local_forward is None and x2.is_cuda and self.fused is not False:
             try:
                 y = self._forward_fused(x2, out_dtype)
@@ -285,6 +291,46 @@ class RowParallelDynamicQuantLinear(nn.Module):
             y = self.ops.epilogue(acc[:, self.n_lo:self.n_hi].contiguous(), s_x, self.weight_scale[self.n_lo:self.n_hi],
                                   self.bias[self.n_lo:self.n_hi] if self.bias is not None else None, out_dtype)
         return y.reshape(*lead, n_out)
+
+
+class ParallelGatedMLP(nn.Module):
+    """Tensor-parallel gated MLP (Llama: down(silu(gate(x)) * up(x))) on the dynamic int8 path, Megatron layout:
+    gate / up column-parallel with NO gather, the activation product computed on the local column slice, down
+    row-parallel with a K-sharded input.  Exchanges per forward: one all-reduce(MAX) of `tokens` floats (the
+    per-token scale of the hidden activation needs the row maximum over all shards) and the fused int32
+    reduce-scatter + all-gather of the down projection.  Because the hidden slices, the global row maxima and the
+    int32 partial sums are all exact, the output is bit-identical to the same three DynamicQuantLinear modules
+    chained on one GPU (with `act_mul_quant`'s definition of the activation product)."""
+
+    def __init__(self, gate, up, down, group=None, act: str = "silu", out_dtype: Optional[torch.dtype] = None,
+                 fused: Optional[bool] = None):
+        """gate, up, down: unsharded DynamicQuantLinear modules (every rank passes the same ones)."""
+        super().__init__()
+        if gate.out_features != up.out_features or down.in_features != gate.out_features:
+            raise ValueError("gate / up / down shapes do not form a gated MLP")
+        self.act = act
+        self.out_dtype = out_dtype
+        kw = dict(group=group, out_dtype=out_dtype)
+        self.gate = ShardedDynamicQuantLinear(gate.qweight, gate.weight_scale, gate.bias, spec=gate.spec,
+                                              gather_output=False, align=16, **kw)
+        self.up = ShardedDynamicQuantLinear(up.qweight, up.weight_scale, up.bias, spec=up.spec,
+                                            gather_output=False, align=16, **kw)
+        self.down = RowParallelDynamicQuantLinear(down.qweight, down.weight_scale, down.bias, spec=down.spec,
+                                                  input_is_sharded=True, gather_output=True, fused=fused, **kw)
+        if (self.gate.lo, self.gate.hi) != (self.down.k_lo, self.down.k_hi):
+            raise ValueError("column shards of gate/up and K shards of down do not line up")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        dt = self.out_dtype or x.dtype
+        xq, s_x = F.quantize_act(x2, spec=self.gate.spec)                 # one quantisation shared by gate and up
+        n = self.gate.hi - self.gate.lo
+        g = F.qgemm(xq, s_x, self.gate.qweight, self.gate.weight_scale, self.gate.bias, dt)[:, :n]
+        u = F.qgemm(xq, s_x, self.up.qweight, self.up.weight_scale, self.up.bias, dt)[:, :n]
+        h = F.act_mul(g, u, self.act)                                      # local slice of the hidden activation
+        y = self.down(h)
+        return y.reshape(*lead, self.down.out_features)
 
 
 def maybe_shard(linear_q, group=None, min_out_features: int = 16384, **kw):

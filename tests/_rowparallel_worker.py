@@ -40,6 +40,40 @@ def main():
                             print(f"rank {rank} MISMATCH N={N} K={K} M={M} fused={fused} sharded_in={sharded_in} gather={gather}")
             if rank == 0:
                 print(f"N={N} K={K} M={M} fused={fused} -> {rp.fused}")
+    # the whole tensor-parallel gated MLP (column-parallel gate/up without a gather -> silu*up on the local slice ->
+    # row-parallel down): bit-identical to the three modules chained on one GPU
+    from protoquant_b200 import functional as F
+    for (H, I, M) in ((4096, 11008, 512), (8192, 28672, 64), (512, 1000 * 16, 33)):
+        gate = pq.DynamicQuantLinear.from_float(torch.nn.Linear(H, I, bias=False).to(torch.bfloat16).cuda())
+        up = pq.DynamicQuantLinear.from_float(torch.nn.Linear(H, I, bias=False).to(torch.bfloat16).cuda())
+        down = pq.DynamicQuantLinear.from_float(torch.nn.Linear(I, H, bias=True).to(torch.bfloat16).cuda())
+        x = torch.randn(M, H, dtype=torch.bfloat16, device="cuda")
+        want = down(F.act_mul(gate(x), up(x), "silu"))
+        mlp = pq.ParallelGatedMLP(gate, up, down)
+        for _ in range(3):
+            same = torch.equal(mlp(x), want)
+            ok = ok and same
+            if not same:
+                print(f"rank {rank} MLP MISMATCH H={H} I={I} M={M}")
+        if rank == 0:
+            print(f"MLP H={H} I={I} M={M} fused={mlp.down.fused}")
+        if (H, I) == (8192, 28672):
+            x2 = torch.randn(2048, H, dtype=torch.bfloat16, device="cuda")
+            for name, fn in (("one_gpu_chain", lambda: down(F.act_mul(gate(x2), up(x2), "silu"))), ("tensor_parallel", lambda: mlp(x2))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([a.elapsed_time(b) / 10], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    print(f"TIMING llama70b_mlp 8192/28672 M=2048 world={dist.get_world_size()} {name}: {t.item()*1e3:.1f} us")
     # timing: Llama-70B down projection 28672 -> 8192 at 2048 tokens
     N, K, M = 8192, 28672, 2048
     lin = torch.nn.Linear(K, N, bias=False).to(torch.bfloat16).cuda()

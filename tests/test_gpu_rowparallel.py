@@ -117,6 +117,19 @@ def test_row_parallel_module_single_rank_equals_unsharded():
     assert torch.equal(rp(x), m(x))
 
 
+def test_parallel_gated_mlp_single_rank_equals_chained_modules():
+    torch.manual_seed(7)
+    H, I, M = 1024, 2816, 100
+    gate = pq.DynamicQuantLinear.from_float(torch.nn.Linear(H, I, bias=False).to(torch.bfloat16).cuda())
+    up = pq.DynamicQuantLinear.from_float(torch.nn.Linear(H, I, bias=False).to(torch.bfloat16).cuda())
+    down = pq.DynamicQuantLinear.from_float(torch.nn.Linear(I, H, bias=True).to(torch.bfloat16).cuda())
+    x = torch.randn(M, H, dtype=torch.bfloat16, device="cuda")
+    want = down(F.act_mul(gate(x), up(x), "silu"))
+    mlp = pq.ParallelGatedMLP(gate, up, down)
+    assert torch.equal(mlp(x), want)
+    assert torch.equal(mlp(x.reshape(4, 25, H)).reshape(M, H), want)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_row_parallel_module_nvlink_bit_identical():
     n = min(torch.cuda.device_count(), 8)
