@@ -19,7 +19,8 @@ class QTensor:
     ``data``  int8  [R, C]  (row stride padded to 16 bytes so it can feed the GEMM directly)
     ``scale`` fp32  [R]     one scale per row: per token for activations, per output channel
                             for weights W[N,K]
-    ``axis``  the reduced axis of the original tensor (always the last one, -1)
+    ``axis``  the reduced axis of the original tensor: -1 (the last one; one scale per row of ``data``) or, for 2-D
+              tensors, 0 (one scale per column of ``data``)
     """
 
     __slots__ = ("data", "scale", "axis", "orig_dtype", "orig_shape")
@@ -41,7 +42,8 @@ class QTensor:
         return self.data.device
 
     def dequantize(self, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-        out = F.dequantize(self.data, self.scale, axis=0, out_dtype=dtype or self.orig_dtype)
+        # axis == -1: one scale per row of `data`; axis == 0 (2-D tensors): one scale per column
+        out = F.dequantize(self.data, self.scale, axis=0 if self.axis == -1 else 1, out_dtype=dtype or self.orig_dtype)
         return out.reshape(self.orig_shape)
 
     def int_repr(self) -> torch.Tensor:
@@ -62,8 +64,13 @@ def quantize(t: torch.Tensor, axis: int = -1, spec: Optional[F.QuantSpec] = None
     ``t`` [..., C] is flattened to [R, C]; each row gets ``scale = absmax/127`` and
     ``q = rne(t / scale)``.  Only ``axis=-1`` (reduce over the last dim) is supported,
     which covers both per-token activations and per-output-channel weights W[N,K]."""
+    if t.dim() == 2 and axis in (0, -2):
+        # reduce over the rows: one scale per column (e.g. a weight stored [K, N]).  The row-wise kernel runs on
+        # the transposed copy; `data` is returned in the original orientation, its scale vector has N entries.
+        q, s = F.quantize_act(t.t().contiguous(), spec=spec)
+        return QTensor(q.t().contiguous(), s, axis=0, orig_dtype=t.dtype, orig_shape=t.shape)
     if axis not in (-1, t.dim() - 1):
-        raise NotImplementedError("QTensor quantisation reduces over the last axis only")
+        raise NotImplementedError("QTensor quantisation reduces over the last axis (any rank) or axis 0 of a 2-D tensor")
     t2 = t.reshape(-1, t.shape[-1])
     q, s = F.quantize_act(t2, spec=spec)
     return QTensor(q, s, axis=-1, orig_dtype=t.dtype, orig_shape=t.shape)

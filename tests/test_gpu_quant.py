@@ -174,3 +174,15 @@ def test_c_abi_direct_call_and_errors():
     assert lib.pq_act_quant(x.data_ptr(), 7, 8, 256, 256, q.data_ptr(), 256, s.data_ptr(), 0, None, st) == 1
     assert lib.pq_act_quant(x.data_ptr(), 0, 8, 256, 128, q.data_ptr(), 256, s.data_ptr(), 0, None, st) == 1
     assert b"ldx" in lib.pq_last_error()
+
+
+def test_qtensor_axis0_per_column_scales():
+    """quantize(t, axis=0): one scale per column; equals the oracle's row-wise quantisation of t^T."""
+    g = torch.Generator().manual_seed(71)
+    t = torch.randn(300, 96, generator=g).to(torch.bfloat16)
+    qt = pq.quantize(t.cuda(), axis=0)
+    q_o, s_o = O.quantize_rowwise(t.t().contiguous())
+    assert qt.axis == 0 and qt.data.shape == (300, 96) and qt.scale.shape == (96,)
+    assert np.array_equal(qt.data.cpu().numpy(), q_o.T) and np.array_equal(qt.scale.cpu().numpy(), s_o)
+    ref = torch.from_numpy(O.dequantize(q_o.T, s_o, axis=1)).to(torch.bfloat16)
+    assert torch.equal(qt.dequantize().cpu(), ref)

@@ -60,7 +60,7 @@ def test_qtensor_metadata():
     assert qt.shape == (2, 3, 8) and qt.axis == -1
     assert "QTensor" in repr(qt)
     with pytest.raises(NotImplementedError):
-        pq.quantize(torch.zeros(4, 4), axis=0)
+        pq.quantize(torch.zeros(4, 4, 4), axis=0)
 
 
 # ---- world_size 2 over gloo ------------------------------------------------------------
