@@ -62,8 +62,10 @@ struct GemmArgs {
                             // rank's inbox on the rank that owns those output columns)
 };
 
-// WS_BYTES: per-warp TMA-store staging of the direct epilogue (16-bit outputs): every epilogue warp owns
-// WS_NBUF boxes of [32 rows x 64 B]; 0 = no staging (fp32 / int32 outputs keep per-lane global stores).
+// WS_BYTES: per-warp TMA-store staging of the direct epilogue: every epilogue warp owns WS_NBUF boxes of
+// [32 rows x 32 columns] (64-byte rows for 16-bit outputs, 128-byte rows for fp32); 0 = no staging (int32
+// outputs, or tile configurations whose operand ring leaves no room, keep per-lane global stores).
+// OUT_BYTES: 2 = bf16 / fp16, 4 = fp32, 0 = int32 accumulators.
 constexpr int NUM_BARS_C(int stages) { return 2 * stages + 4; }
 template <int CG, int BN, int STAGES, bool STAGED = false, int OUT_BYTES = 4>
 struct SmemLayout {
@@ -76,9 +78,9 @@ struct SmemLayout {
   static constexpr int STAGE_OUT = STAGED ? 2 * 32768 : 0;  // per column-half [128 rows][256 B] output staging
   static constexpr int OFF_STAGE_OUT = OFF_B + STAGES * B_STAGE;
   static constexpr int BNP = (BN + 31) / 32 * 32;           // columns rounded up to whole 32-column chunks
-  static constexpr int WS_BOX = 32 * 64;                    // one warp's box: 32 rows x 32 sixteen-bit columns
+  static constexpr int WS_BOX = 32 * 32 * (OUT_BYTES == 4 ? 4 : 2);   // one warp's box: 32 rows x 32 columns
   static constexpr int WS_FIXED = STAGES * (A_STAGE + B_STAGE) + 4 * BNP * 4 + NUM_BARS_C(STAGES) * 8 + 16 + 1024;
-  static constexpr int WS_NBUF = (OUT_BYTES != 2 || STAGED) ? 0 : (WS_FIXED + 2 * 8 * WS_BOX <= 227 * 1024) ? 2
+  static constexpr int WS_NBUF = (OUT_BYTES == 0 || STAGED) ? 0 : (WS_FIXED + 2 * 8 * WS_BOX <= 227 * 1024) ? 2
                                  : (WS_FIXED + 8 * WS_BOX <= 227 * 1024) ? 1 : 0;
   static constexpr int WS_BYTES = WS_NBUF * 8 * WS_BOX;
   static constexpr int OFF_WS = OFF_STAGE_OUT + STAGE_OUT;  // 1024-aligned: every term before it is
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
              const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_y, const GemmArgs g) {
-  using L = SmemLayout<CG, BN, STAGES, STAGED, (int)sizeof(OutT)>;
+  using L = SmemLayout<CG, BN, STAGES, STAGED, std::is_same<OutT, int32_t>::value ? 0 : (int)sizeof(OutT)>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
   static_assert(!STAGED || BN == 256, "staged epilogue assumes 128-column halves");
   static_assert(MC == 1 || (MC == 2 && CG == 2 && (BN / 4) % 8 == 0), "multicast clusters are pairs of CTA pairs");
@@ -651,10 +653,13 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int buf = (L::WS_NBUF == 2) ? ((c - c_lo) & 1) : 0;
             if (lane == 0) tma_store_wait_read<(L::WS_NBUF > 1) ? L::WS_NBUF - 1 : 0>();   // the box is free again
             __syncwarp();
-            uint8_t* box = ws_gen + buf * L::WS_BOX + lane * 64;
+            // row pitch 64 B (16-bit, 64B swizzle: unit ^ ((row >> 1) & 3)) or 128 B (fp32, 128B swizzle: unit ^ (row & 7))
+            constexpr int UNITS = OutPack<OT>::WORDS / 4;
+            uint8_t* box = ws_gen + buf * L::WS_BOX + lane * (UNITS * 16);
+            const int swz = (UNITS == 4) ? (((int)lane >> 1) & 3) : ((int)lane & 7);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(box + ((i ^ (((int)lane >> 1) & 3)) << 4)) =
+            for (int i = 0; i < UNITS; ++i)
+              *reinterpret_cast<uint4*>(box + ((i ^ swz) << 4)) =
                   make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             fence_proxy_async_smem();
             __syncwarp();
@@ -830,7 +835,7 @@ SkSlot* sk_get_slot(int dev, int num_sms, cudaStream_t st) {
 template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false, int MC = 1>
 int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g0,
                int num_sms, cudaStream_t st) {
-  using L = SmemLayout<CG, BN, STAGES, STAGED, (int)sizeof(OutT)>;
+  using L = SmemLayout<CG, BN, STAGES, STAGED, std::is_same<OutT, int32_t>::value ? 0 : (int)sizeof(OutT)>;
   GemmArgs g = g0;
   g.num_m_blocks = (g.M + BLOCK_M * CG * MC - 1) / (BLOCK_M * CG * MC);
   g.num_n_blocks = (g.N + BN - 1) / BN;
@@ -858,15 +863,17 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) g.tma_store = 1;
   } else if (L::WS_NBUF > 0 && g.n_out == 1 && g.vec_ok && g_tma_store) {
-    // per-warp epilogue boxes: [32 rows] x [32 sixteen-bit columns], 64B swizzle
+    // per-warp epilogue boxes: [32 rows] x [32 columns]; 64B swizzle for 16-bit outputs, 128B swizzle for fp32
+    constexpr int esz = (int)sizeof(OutT);
     auto fn = get_encode_fn();
     if (!fn) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
-    cuuint64_t strides[1] = {(cuuint64_t)(g.ldo * 2)};
+    cuuint64_t strides[1] = {(cuuint64_t)(g.ldo * esz)};
     cuuint32_t box[2] = {32, 32};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&ty, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, g.out[0], dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+    CUresult r = fn(&ty, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, g.out[0], dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    esz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) g.tma_store = 1;
   }

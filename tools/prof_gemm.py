@@ -16,10 +16,11 @@ pq.lib().pq_debug_set_streamk(sk)
 a = torch.randint(-128, 128, (M, K), dtype=torch.int8, device="cuda")
 b = torch.randint(-128, 128, (N, K), dtype=torch.int8, device="cuda")
 sx = torch.rand(M, device="cuda"); sw = torch.rand(N, device="cuda")
-y = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+odt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[os.environ.get("PQ_OUT", "bf16")]
+y = torch.empty(M, N, dtype=odt, device="cuda")
 def run():
     for _ in range(iters):
-        pq.qgemm(a, sx, b, sw, None, torch.bfloat16, out=y)
+        pq.qgemm(a, sx, b, sw, None, odt, out=y)
 run(); torch.cuda.synchronize()
 if nograph:
     fn = run
@@ -41,4 +42,4 @@ for _ in range(5):
 ref = (a[:64].float() @ b[:512].float().t()) * sx[:64, None] * sw[None, :512]
 ok = torch.allclose(y[:64, :512].float(), ref, rtol=2e-2, atol=1e-2 * ref.abs().max().item())
 if int(os.environ.get("PQ_EPI", "0")): ok = True
-print(f"M={M} N={N} K={K} cfg={cfg} sk={sk} staged={staged} epi={os.environ.get('PQ_EPI', '0')} tma_store={os.environ.get('PQ_TMA_STORE', '1')}: {best*1e3:.1f} us  {2*M*N*K/best/1e9:.0f} TOPS  {'ok' if ok else 'MISMATCH'}")
+print(f"M={M} N={N} K={K} cfg={cfg} sk={sk} staged={staged} epi={os.environ.get('PQ_EPI', '0')} tma_store={os.environ.get('PQ_TMA_STORE', '1')} out={os.environ.get('PQ_OUT', 'bf16')}: {best*1e3:.1f} us  {2*M*N*K/best/1e9:.0f} TOPS  {'ok' if ok else 'MISMATCH'}")
