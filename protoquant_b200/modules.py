@@ -5,6 +5,7 @@ Weights are quantised once, per output channel, when the module is built.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -13,6 +14,8 @@ from torch import nn
 from . import _lib
 from . import functional as F
 from .qtensor import QTensor
+
+_NVTX = os.environ.get("PQ_NVTX", "0") not in ("", "0")
 
 
 class DynamicQuantLinear(nn.Module):
@@ -62,6 +65,15 @@ class DynamicQuantLinear(nn.Module):
                        out_dtype or self.out_dtype or torch.bfloat16, out=out)
 
     def forward(self, x) -> torch.Tensor:
+        if _NVTX:      # PQ_NVTX=1: one range per linear so that nsys / ncu timelines show the two launches together
+            torch.cuda.nvtx.range_push(f"pq.DynamicQuantLinear[{self.in_features}->{self.out_features}]")
+            try:
+                return self._forward(x)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return self._forward(x)
+
+    def _forward(self, x) -> torch.Tensor:
         # A QTensor (or an (int8, scale) pair) is an activation that is already quantised per token.
         if isinstance(x, QTensor):
             y = self.forward_quantized(x.data, x.scale, self.out_dtype or x.orig_dtype)
