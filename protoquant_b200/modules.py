@@ -106,6 +106,31 @@ class DynamicQuantLinear(nn.Module):
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, int8"
 
 
+def fuse_linears(mods) -> DynamicQuantLinear:
+    """One DynamicQuantLinear computing several linears that read the SAME input (q/k/v, gate/up): the int8
+    weights, per-channel scales and biases are concatenated along the output dimension, so the activation is
+    quantised once and one GEMM runs instead of len(mods).  Per-output-channel scales make this exact: the fused
+    output is the concatenation of the separate outputs, bit for bit (split it with `y.split(sizes, -1)`)."""
+    mods = list(mods)
+    if not mods:
+        raise ValueError("fuse_linears needs at least one module")
+    K = mods[0].in_features
+    if any(m.in_features != K for m in mods):
+        raise ValueError("fused linears must share in_features")
+    if any((m.bias is None) != (mods[0].bias is None) for m in mods):
+        raise ValueError("fused linears must all have a bias or all have none")
+    if any(m.spec != mods[0].spec or m.out_dtype != mods[0].out_dtype for m in mods):
+        raise ValueError("fused linears must share the quantisation spec and output dtype")
+    dev = mods[0].qweight_storage.device
+    fused = DynamicQuantLinear(K, sum(m.out_features for m in mods), mods[0].bias is not None, device=dev,
+                               out_dtype=mods[0].out_dtype, spec=mods[0].spec)
+    fused.qweight_storage.copy_(torch.cat([m.qweight_storage for m in mods], dim=0))
+    fused.weight_scale.copy_(torch.cat([m.weight_scale for m in mods]))
+    if fused.bias is not None:
+        fused.bias.copy_(torch.cat([m.bias for m in mods]))
+    return fused
+
+
 def swap_linear(model: nn.Module, min_features: int = 0, out_dtype: Optional[torch.dtype] = None,
                 spec: Optional[F.QuantSpec] = None, skip=()) -> nn.Module:
     """Replace every nn.Linear (in/out features >= min_features, name not in `skip`) in place."""

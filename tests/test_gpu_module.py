@@ -90,6 +90,16 @@ def test_host_buffer_c_api_roundtrip():
         lib.pq_linear_destroy(h)
 
 
+def test_fused_linears_equal_the_separate_linears_bit_for_bit():
+    torch.manual_seed(9)
+    qkv = [pq.DynamicQuantLinear.from_float(nn.Linear(1024, n).to(torch.bfloat16).cuda()) for n in (1024, 256, 256)]
+    fused = pq.fuse_linears(qkv)
+    x = torch.randn(300, 1024, dtype=torch.bfloat16, device="cuda")
+    parts = fused(x).split([1024, 256, 256], dim=-1)
+    for m, y in zip(qkv, parts):
+        assert torch.equal(m(x), y)
+
+
 def test_sharded_module_single_rank_equals_unsharded():
     torch.manual_seed(3)
     lin = nn.Linear(512, 1000).to(torch.bfloat16).cuda()

@@ -55,6 +55,20 @@ def test_compat_alias_table():
         assert hasattr(compat, name)
 
 
+def test_fuse_linears_concatenates_per_channel_parameters():
+    a, b = pq.DynamicQuantLinear(64, 32), pq.DynamicQuantLinear(64, 48)
+    a.qweight_storage.random_(-127, 128); b.qweight_storage.random_(-127, 128)
+    a.weight_scale.uniform_(0.1, 1.0); b.weight_scale.uniform_(0.1, 1.0)
+    a.bias.normal_(); b.bias.normal_()
+    f = pq.fuse_linears([a, b])
+    assert (f.in_features, f.out_features) == (64, 80)
+    assert torch.equal(f.qweight[:32], a.qweight) and torch.equal(f.qweight[32:], b.qweight)
+    assert torch.equal(f.weight_scale, torch.cat([a.weight_scale, b.weight_scale]))
+    assert torch.equal(f.bias, torch.cat([a.bias, b.bias]))
+    with pytest.raises(ValueError):
+        pq.fuse_linears([a, pq.DynamicQuantLinear(32, 8)])
+
+
 def test_qtensor_metadata():
     qt = pq.QTensor(torch.zeros(6, 8, dtype=torch.int8), torch.ones(6), orig_dtype=torch.bfloat16, orig_shape=(2, 3, 8))
     assert qt.shape == (2, 3, 8) and qt.axis == -1
