@@ -129,7 +129,8 @@ int pq_qlinear(const void* x, int x_dtype, int64_t ldx,
   if (rc) return rc;
   // M > 64: the tcgen05 GEMM re-reads each weight tile from L2 once per 256 tokens; have the quantizer
   // pull the (DRAM-cold) weights into L2 meanwhile.  Capped well below the 126 MB L2.
-  const long long w_bytes = (M > 64 && Wq && N > 0) ? (long long)N * ldb : 0;
+  // (bytes of the [N, K] view: the last row ends after K bytes even when its stride is larger)
+  const long long w_bytes = (M > 64 && Wq && N > 0 && ldb >= K) ? (long long)(N - 1) * ldb + K : 0;
   rc = launch_rowwise_quant(x, x_dtype, M, K, ldx, xq_ws, ldq, sx_ws, 0, resolve_spec(spec), (cudaStream_t)stream,
                             Wq, w_bytes < (64LL << 20) ? w_bytes : (64LL << 20));
   if (rc) return rc;
