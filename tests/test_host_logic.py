@@ -69,6 +69,23 @@ def test_fuse_linears_concatenates_per_channel_parameters():
         pq.fuse_linears([a, pq.DynamicQuantLinear(32, 8)])
 
 
+def test_parallel_mlp_shards_line_up_and_has_no_cpu_path():
+    gate, up, down = pq.DynamicQuantLinear(64, 160, bias=False), pq.DynamicQuantLinear(64, 160, bias=False), pq.DynamicQuantLinear(160, 64)
+    mlp = pq.ParallelGatedMLP(gate, up, down)
+    assert (mlp.gate.lo, mlp.gate.hi) == (mlp.down.k_lo, mlp.down.k_hi) == (0, 160)
+    assert mlp.gate.gather_output is False and mlp.down.input_is_sharded is True
+    with pytest.raises(pq.ProtoquantError, match="no CPU fallback"):
+        mlp(torch.randn(4, 64))
+    with pytest.raises(ValueError):
+        pq.ParallelGatedMLP(gate, up, pq.DynamicQuantLinear(128, 64))
+    for world in (2, 4, 8):          # column shards of gate/up == K shards of down for every rank
+        for n in (11008, 28672, 16000, 1000):
+            for r in range(world):
+                assert pq.shard_bounds(n, world, r, align=16) == pq.shard_bounds(n, world, r, 16)
+                lo, hi = pq.shard_bounds(n, world, r, align=16)
+                assert lo % 16 == 0 and 0 <= lo <= hi <= n
+
+
 def test_qtensor_metadata():
     qt = pq.QTensor(torch.zeros(6, 8, dtype=torch.int8), torch.ones(6), orig_dtype=torch.bfloat16, orig_shape=(2, 3, 8))
     assert qt.shape == (2, 3, 8) and qt.axis == -1
