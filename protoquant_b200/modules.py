@@ -11,7 +11,6 @@ from typing import Optional
 import torch
 from torch import nn
 
-from . import _lib
 from . import functional as F
 from .qtensor import QTensor
 
