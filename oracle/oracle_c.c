@@ -68,3 +68,41 @@ void pqo_dequant_f32(const int8_t* q, const float* s, int axis, int64_t rows, in
       out[r * cols + c] = v;
     }
 }
+
+/* Row-parallel (K-split) pieces, SURVEY.md §8f-3.  A K-shard quantises its column slice with the maximum of
+ * the WHOLE row (amax_in, after the cross-shard max), so codes and scale equal those of the unsplit quantizer. */
+void pqo_quantize_rowwise_amax_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* amax_in,
+                                   int scale_mode, float eps, int qmin, int8_t* q, int64_t ldq, float* s_out) {
+  for (int64_t r = 0; r < rows; ++r) {
+    const float* xr = x + r * ldx;
+    float amax = amax_in[r];
+    if (eps > 0.f && amax < eps) amax = eps;
+    volatile float s = amax / 127.0f;
+    if (amax == 0.f) s = 1.0f;
+    s_out[r] = s;
+    volatile float inv = (scale_mode == 2) ? (amax == 0.f ? 1.0f : 127.0f / amax) : 1.0f / s;
+    for (int64_t c = 0; c < cols; ++c) {
+      volatile float t = (scale_mode == 0) ? xr[c] / s : xr[c] * inv;
+      float v = nearbyintf(t);
+      if (v < (float)qmin) v = (float)qmin;
+      if (v > 127.f) v = 127.f;
+      q[r * ldq + c] = (int8_t)v;
+    }
+  }
+}
+
+/* y = ((float(sum_p part_p) * s_x[m]) * s_w[n]) + bias[n]: the reduce + dequant half of the fused
+ * GEMM + reduce-scatter.  parts is [n_parts][M][N] int32; the sum is exact. */
+void pqo_reduce_epilogue_f32(const int32_t* parts, int n_parts, const float* s_x, const float* s_w, const float* bias,
+                             int64_t M, int64_t N, float* y) {
+  for (int64_t m = 0; m < M; ++m)
+    for (int64_t n = 0; n < N; ++n) {
+      int32_t acc = 0;
+      for (int p = 0; p < n_parts; ++p) acc += parts[((int64_t)p * M + m) * N + n];
+      volatile float v = (float)acc;
+      v = v * s_x[m];
+      v = v * s_w[n];
+      if (bias) v = v + bias[n];
+      y[m * N + n] = v;
+    }
+}

@@ -188,3 +188,45 @@ def test_producer_op_references_match_torch_float64():
                     ("gelu_tanh", lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
         assert np.allclose(O.act_mul_ref(x.float(), w.expand(6, 96).float(), act), (fn(x) * w).numpy(), rtol=1e-5, atol=1e-6)
         assert np.allclose(O.act_mul_ref(x.float(), None, act), fn(x).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_k_split_dataflow_equals_unsplit_linear_numpy_and_c(clib):
+    """SURVEY.md §8f-3 on the CPU: K-shards quantise their slices with the global row maximum, multiply, and the
+    int32 partial sums are reduced before ONE epilogue -- the result has the bits of the unsplit linear, in the numpy
+    oracle and in the independent C restatement alike."""
+    torch.manual_seed(11)
+    M, N, K, G = 9, 21, 208, 4
+    x = torch.randn(M, K).to(torch.bfloat16)
+    x[0, K - 1] = 60.0                                   # row maximum in the last shard
+    w = (torch.rand(N, K) * 2 - 1) / K ** 0.5
+    b = torch.randn(N)
+    wq, sw = O.quantize_rowwise(w)
+    full = O.qlinear(x, wq, sw, b.numpy(), out_dtype="f32").numpy()
+    x32 = np.ascontiguousarray(O.to_f32(x))
+    amax = np.max(np.abs(x32), axis=-1).astype(np.float32)
+    per = 64
+    parts = np.zeros((G, M, N), np.int32)
+    s_x = None
+    for r in range(G):
+        lo, hi = min(r * per, K), min((r + 1) * per, K)
+        q_np, s_x = O.quantize_rowwise(x32[:, lo:hi], amax=amax)
+        xs = np.ascontiguousarray(x32[:, lo:hi])
+        q_c = np.empty((M, hi - lo), np.int8)
+        s_c = np.empty((M,), np.float32)
+        clib.pqo_quantize_rowwise_amax_f32(xs.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(M), ctypes.c_int64(hi - lo),
+                                           ctypes.c_int64(hi - lo), amax.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(0),
+                                           ctypes.c_float(0.0), ctypes.c_int(-128), q_c.ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.c_int64(hi - lo), s_c.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(q_np, q_c) and np.array_equal(s_x, s_c)
+        parts[r] = O.int_mm(q_np, np.ascontiguousarray(wq[:, lo:hi]))
+    # the slices' codes are exactly the columns of the unsplit quantisation
+    q_full, s_full = O.quantize_rowwise(x)
+    assert np.array_equal(s_x, s_full)
+    y_np = O.dequant_epilogue(parts.sum(0, dtype=np.int32), s_x, sw, b.numpy())
+    y_c = np.empty((M, N), np.float32)
+    bias = b.numpy().astype(np.float32)
+    clib.pqo_reduce_epilogue_f32(parts.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(G), s_x.ctypes.data_as(ctypes.c_void_p),
+                                 sw.ctypes.data_as(ctypes.c_void_p), bias.ctypes.data_as(ctypes.c_void_p),
+                                 ctypes.c_int64(M), ctypes.c_int64(N), y_c.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(y_np.view(np.uint32), full.view(np.uint32))
+    assert np.array_equal(y_c.view(np.uint32), full.view(np.uint32))
