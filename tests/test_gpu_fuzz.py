@@ -12,7 +12,7 @@ import protoquant_oracle as O
 pytestmark = pytest.mark.gpu
 
 DTS = [torch.bfloat16, torch.float16, torch.float32]
-COMMON = dict(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+COMMON = dict(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 
 
 def _x(rows, K, dt, seed, pad=0):
