@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprotoquant_b200.so")
+# PQ_LIB_PATH: development override (A/B builds of the same ABI, e.g. tools/ab_build.sh); the product loads the in-tree library
+LIB_PATH = os.environ.get("PQ_LIB_PATH") or os.path.join(_HERE, "libprotoquant_b200.so")
 
 PQ_F32, PQ_F16, PQ_BF16, PQ_I32 = 0, 1, 2, 3
 PQ_DIV, PQ_RCP_MUL, PQ_INV_SCALE = 0, 1, 2

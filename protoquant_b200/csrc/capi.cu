@@ -10,7 +10,7 @@ namespace pq {
 
 static thread_local char tl_error[512] = "";
 std::atomic<uint64_t> g_launch_count{0};
-int g_pdl = 1;
+Knob g_pdl{1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;

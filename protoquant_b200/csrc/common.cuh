@@ -15,7 +15,18 @@ namespace pq {
 // ---- error plumbing (thread-local message, see pq_last_error) -------------------
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launch_count;
-extern int g_pdl;   // 1 = launch kernels with programmatic stream serialization (default)
+
+// Test / profiling knobs behind the exported pq_debug_* hooks (not part of the API declared in the header).  They are
+// process-wide relaxed atomics: safe to flip from any thread, and every value selects between code paths that
+// produce bit-identical results (tile shapes, schedules, store instructions) or a profiling mode.
+struct Knob {
+  std::atomic<int> v;
+  constexpr Knob(int x) : v(x) {}
+  operator int() const { return v.load(std::memory_order_relaxed); }
+  int load(std::memory_order = std::memory_order_relaxed) const { return v.load(std::memory_order_relaxed); }
+  void operator=(int x) { v.store(x, std::memory_order_relaxed); }
+};
+extern Knob g_pdl;   // 1 = launch kernels with programmatic stream serialization (default)
 
 #define PQ_FAIL(code, ...)        \
   do {                            \

@@ -16,6 +16,20 @@ __device__ __forceinline__ uint32_t lane_id() {
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
   return l;
 }
+// True in exactly one (the lowest active) lane of a converged warp.  Unlike `lane == 0`, ptxas knows that the code
+// guarded by elect.sync runs in a single thread, so descriptor / barrier operands of the tcgen05 and TMA
+// instructions inside it go straight to uniform registers instead of through an ELECT + R2UR.BROADCAST +
+// BRA.U.ANY "waterfall" per instruction (measured: ~150 SASS instructions per k-block in the MMA issue loop,
+// which made the single issuing thread -- not the tensor pipe -- the bottleneck of the main loop).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)::"memory");
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -98,6 +112,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is incomplete)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a
 // hung GPU.  The bound is wall-clock (globaltimer), checked every 1024 failed polls.
 #ifndef PQ_MBAR_TIMEOUT_NS
@@ -164,6 +190,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
+}
+// One 16-byte store to an NVSwitch multicast address: the switch replicates it into every GPU of the multicast
+// group (plain st to a multimem address is undefined; multimem.st is the instruction NVLS defines for it).
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -17,7 +17,7 @@
 #include "quant_math.cuh"
 
 namespace pq {
-int g_fused_decode = 0;   // pq_debug_set_fused_decode; OFF: measured slower than quant kernel + PDL (profiles/README_r1.md)
+Knob g_fused_decode{0};   // pq_debug_set_fused_decode; OFF: measured slower than quant kernel + PDL (profiles/README_r1.md)
 namespace {
 
 using namespace ptx;
@@ -563,10 +563,9 @@ int launch_fused(const int8_t* b, int64_t ldb, FusedArgs g, int S, cudaStream_t 
   int rc = make_tmap(&tw, b, g.N, g.K, ldb, TILE_N);
   if (rc) return rc;
   auto kern = qlinear_smallm_fused_kernel<T, MP, STAGES, OutT>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+  static PerDeviceOnce once;   // per device: a process may drive several GPUs
+  const cudaError_t attr_err = once.run([&](int*) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
   });
   if (attr_err != cudaSuccess)
     PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));
@@ -617,10 +616,9 @@ int launch_small(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, Sma
   rc = make_tmap(&tx, a, g.M, g.K, lda, MP);
   if (rc) return rc;
   auto kern = qgemm_smallm_kernel<MP, STAGES, OutT>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+  static PerDeviceOnce once;   // per device: a process may drive several GPUs
+  const cudaError_t attr_err = once.run([&](int*) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
   });
   if (attr_err != cudaSuccess)
     PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));

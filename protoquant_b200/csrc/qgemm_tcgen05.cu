@@ -57,6 +57,7 @@ struct GemmArgs {
   int prefetch_b;           // 1 = warp 3 prefetches this CTA's weight boxes into L2 ahead of the ring
   int tma_store;            // staged epilogue hands its tiles to TMA bulk stores (single destination)
   int dbg;                  // profiling only (pq_debug_set_epilogue): bit 0 = the epilogue skips its global stores
+  int multimem;             // out[0] is an NVSwitch multicast address: the LSU copy-out uses multimem.st
   int scatter_cols;         // > 0 (staged epilogue): columns [d*scatter_cols, (d+1)*scatter_cols) go to out[d] ONLY, as a
                             // [M, scatter_cols] matrix with row stride ldo (fused GEMM + reduce-scatter: out[d] is this
                             // rank's inbox on the rank that owns those output columns)
@@ -67,6 +68,15 @@ struct GemmArgs {
 // outputs, or tile configurations whose operand ring leaves no room, keep per-lane global stores).
 // OUT_BYTES: 2 = bf16 / fp16, 4 = fp32, 0 = int32 accumulators.
 constexpr int NUM_BARS_C(int stages) { return 2 * stages + 4; }
+
+// Output tensor maps.  The staged epilogue (fused all-gather / reduce-scatter) can hand its shared-memory tile to
+// TMA bulk stores towards up to 8 destinations (the local buffer and the peers' buffers over NVLink), so it takes
+// one tensor map per destination; every other instantiation needs a single map.
+struct OutMaps { CUtensorMap m[8]; };
+template <bool STAGED> struct YMap { using type = CUtensorMap; };
+template <> struct YMap<true> { using type = OutMaps; };
+__device__ __forceinline__ const CUtensorMap* ymap(const CUtensorMap& t, int) { return &t; }
+__device__ __forceinline__ const CUtensorMap* ymap(const OutMaps& t, int d) { return &t.m[d]; }
 template <int CG, int BN, int STAGES, bool STAGED = false, int OUT_BYTES = 4>
 struct SmemLayout {
   static constexpr int A_STAGE = BLOCK_M * BLOCK_K;
@@ -174,7 +184,8 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
-#define PQ_TL(i) do { if (g.tl) g.tl[(size_t)blockIdx.x * 32 + (i)] = globaltimer_ns(); } while (0)
+constexpr int TL_STRIDE = 40;   // u64 slots per CTA in the debug timeline: 0..31 %globaltimer stamps, 32/33 clock64 at start/end
+#define PQ_TL(i) do { if (g.tl) g.tl[(size_t)blockIdx.x * TL_STRIDE + (i)] = globaltimer_ns(); } while (0)
 
 // STAGED = true: the epilogue goes through shared memory so that every global store
 // instruction writes whole 256-byte row segments (needed for NVLink peer / multicast
@@ -187,7 +198,7 @@ template <int CG, int BN, int STAGES, typename OutT, bool STAGED = false, int MC
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
              const __grid_constant__ CUtensorMap tmap_b,
-             const __grid_constant__ CUtensorMap tmap_y, const GemmArgs g) {
+             const __grid_constant__ typename YMap<STAGED>::type tmap_y, const GemmArgs g) {
   using L = SmemLayout<CG, BN, STAGES, STAGED, std::is_same<OutT, int32_t>::value ? 0 : (int)sizeof(OutT)>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
   static_assert(!STAGED || BN == 256, "staged epilogue assumes 128-column halves");
@@ -207,7 +218,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: ptxas then knows it is warp-uniform (role dispatch on uniform branches)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const uint32_t lane = lane_id();
   const uint32_t cl_rank = (CG * MC > 1) ? cluster_ctarank() : 0u;   // rank in the cluster
   const uint32_t cta_rank = cl_rank & (CG - 1);                      // rank inside the MMA pair
@@ -234,7 +246,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     PQ_TL(0);
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    if (g.tma_store) prefetch_tmap(&tmap_y);
+    if (g.tma_store) {
+      const int nmaps = STAGED ? g.n_out : 1;
+      for (int d = 0; d < nmaps; ++d) prefetch_tmap(ymap(tmap_y, d));
+    }
   }
   if (warp == 1 && lane == 0) {
     *prod_count = 0;
@@ -266,12 +281,13 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int cluster_id = blockIdx.x / (CG * MC);
   Sched sched;
   sched.init(g, cluster_id, num_clusters);
-  if (threadIdx.x == 0) PQ_TL(1);
+  if (threadIdx.x == 0) { PQ_TL(1); if (g.tl) g.tl[(size_t)blockIdx.x * TL_STRIDE + 32] = (unsigned long long)clock64(); }
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t stage = 0, phase = 0;
+      bool first = true;
       int tile, kb0, kb1;
       while (sched.next(tile, kb0, kb1)) {
         int m_blk, n_blk;
@@ -301,8 +317,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive_remote(fb, leader_rank);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          *prod_count = *prod_count + 1;
-          if (g.tl && g.tl[(size_t)blockIdx.x * 32 + 2] == 0) PQ_TL(2);
+          if (g.prefetch_b) *prod_count = *prod_count + 1;   // only the (off by default) L2 prefetcher reads it
+          if (first) { first = false; PQ_TL(2); }
         }
       }
       PQ_TL(3);
@@ -333,27 +349,38 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
+    // One ELECTED lane runs the whole loop.  With the loop under `lane == 0` instead, ptxas did not know the region
+    // is single-threaded and sent every UTCIMMA / UTCBAR operand through an ELECT + R2UR.BROADCAST + BRA.U.ANY
+    // waterfall (~150 SASS instructions per k-block for the 2-CTA kernel): the issuing thread, not the tensor
+    // pipe, paced the main loop (ncu: tensor pipe 69 % active next to cuBLASLt's 84 % with the same tile shape
+    // and operand traffic; 2048x11008x4096 66.6 -> 59.2 us, 8192^3 357 -> 323 us once fixed).
+    if (leader && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc(UMMA_M, UMMA_N);
+      // descriptor words: the high word is constant; the low word is (address >> 4) of the slot (+2 per 32-byte K step)
+      const uint64_t desc_hi = make_smem_desc(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lo0 = ((smem_base + L::OFF_A) & 0x3FFFFu) >> 4;
+      const uint32_t b_lo0 = ((smem_base + L::OFF_B) & 0x3FFFFu) >> 4;
       uint32_t stage = 0, phase = 0;
       int iter = 0;
+      bool first = true;   // debug timeline: stamp of the first k-block whose operands have landed
       int tile, kb0, kb1;
       for (; sched.next(tile, kb0, kb1); ++iter) {
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(bar_tempty + as * 8, aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * TSTRIDE;
+        uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
-          if (g.tl && g.tl[(size_t)blockIdx.x * 32 + 4] == 0) PQ_TL(4);
-          const uint64_t adesc = make_smem_desc(smem_base + L::OFF_A + stage * L::A_STAGE);
-          const uint64_t bdesc = make_smem_desc(smem_base + L::OFF_B + stage * L::B_STAGE);
+          if (first) { first = false; PQ_TL(4); }
+          const uint64_t adesc = desc_hi | (uint64_t)(a_lo0 + stage * (L::A_STAGE >> 4));
+          const uint64_t bdesc = desc_hi | (uint64_t)(b_lo0 + stage * (L::B_STAGE >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            mma_i8<CG>(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
-                       idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            mma_i8<CG>(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc, accumulate);
+            accumulate = 1;
           }
           tc_commit<CG>(bar_empty + stage * 8, all_mask);
           if (kb == kb1 - 1) tc_commit<CG>(bar_tfull + as * 8, pair_mask);
@@ -411,7 +438,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (etid == 0) *misc_smem = atomicAdd(ctr, 1);
         named_bar_sync(1, EPI_THREADS);
         role = (*misc_smem == lw - fw) ? 2 : 1;
-        if (etid == 0 && iter < 5) { PQ_TL(8 + iter * 4 + 1); if (g.tl) g.tl[(size_t)blockIdx.x * 32 + 28 + (iter & 3)] = (unsigned long long)role * 1000 + (lw - fw + 1); }
+        if (etid == 0 && iter < 5) { PQ_TL(8 + iter * 4 + 1); if (g.tl) g.tl[(size_t)blockIdx.x * TL_STRIDE + 28 + (iter & 3)] = (unsigned long long)role * 1000 + (lw - fw + 1); }
       }
       if (role == 1) {
         tc_fence_after();
@@ -550,8 +577,24 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             fence_proxy_async_smem();
             if (half == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
             if (gt == 0 && m0 < g.M) {
-              if (colp < g.N) tma_store_2d(&tmap_y, stg_u32, colp, m0);
-              if (colp + 128 / ESZ < g.N) tma_store_2d(&tmap_y, stg_u32 + SUB, colp + 128 / ESZ, m0);
+              constexpr int SUBC = 128 / ESZ;                      // columns per sub-box
+              if (g.scatter_cols > 0) {
+                // reduce-scatter: a sub-box belongs to exactly one destination (scatter_cols % SUBC == 0)
+#pragma unroll
+                for (int sb = 0; sb < 2; ++sb) {
+                  const int cs = colp + sb * SUBC;
+                  if (cs < g.N) {
+                    const int d = cs / g.scatter_cols;
+                    tma_store_2d(ymap(tmap_y, d), stg_u32 + sb * SUB, cs - d * g.scatter_cols, m0);
+                  }
+                }
+              } else {
+                // all-gather: the same tile goes to every destination (local buffer + NVLink peers)
+                for (int d = 0; d < g.n_out; ++d) {
+                  if (colp < g.N) tma_store_2d(ymap(tmap_y, d), stg_u32, colp, m0);
+                  if (colp + SUBC < g.N) tma_store_2d(ymap(tmap_y, d), stg_u32 + SUB, colp + SUBC, m0);
+                }
+              }
               tma_store_commit();
             }
           } else {
@@ -578,8 +621,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       if (gcol + e < g.N) dst[e] = ev[e];
                   }
                 } else if (g.vec_ok && gcol + EPU <= g.N) {
-                  for (int d = 0; d < g.n_out; ++d)
-                    *reinterpret_cast<uint4*>(reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol) = v;
+                  if (g.multimem) {
+                    multimem_st_v4(reinterpret_cast<OT*>(g.out[0]) + (long long)grow * g.ldo + gcol, v.x, v.y, v.z, v.w);
+                  } else {
+                    for (int d = 0; d < g.n_out; ++d)
+                      *reinterpret_cast<uint4*>(reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol) = v;
+                  }
                 } else {
                   const OT* ev = reinterpret_cast<const OT*>(&v);
                   for (int d = 0; d < g.n_out; ++d) {
@@ -665,7 +712,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             __syncwarp();
             if (lane == 0) {
               if (row0 < g.M && col0 + ct < g.N && !(g.dbg & 1))
-                tma_store_2d(&tmap_y, ws_u32 + buf * L::WS_BOX, col0 + ct, row0);
+                tma_store_2d(ymap(tmap_y, 0), ws_u32 + buf * L::WS_BOX, col0 + ct, row0);
               tma_store_commit();
             }
           }
@@ -757,14 +804,17 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       else mbar_arrive_remote(bar_tempty + as * 8, leader_rank);
     }
     if constexpr (STAGED) {
-      if (g.tma_store && (etid & 127) == 0) tma_store_wait<0>();   // staging smem must outlive the bulk stores
+      if (g.tma_store && (etid & 127) == 0) {
+        tma_store_wait<0>();   // staging smem must outlive the bulk stores; peer writes are complete after this
+        if (g.n_out > 1 || g.scatter_cols > 0) __threadfence_system();
+      }
     } else if constexpr (L::WS_NBUF > 0) {
       if (g.tma_store && lane == 0) tma_store_wait<0>();
     }
   }
 
   __syncwarp();
-  if (threadIdx.x == 0) PQ_TL(6);
+  if (threadIdx.x == 0) { PQ_TL(6); if (g.tl) g.tl[(size_t)blockIdx.x * TL_STRIDE + 33] = (unsigned long long)clock64(); }
   tc_fence_before();
   if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
@@ -786,9 +836,10 @@ struct SkPool {
   int count = 0;
 };
 SkPool g_sk_pool[64];
-unsigned long long* g_timeline = nullptr;
-int g_tma_store = 1;     // staged epilogue uses TMA bulk stores when it can (pq_debug_set_tma_store)
-int g_sk_mode = -1;  // -1 heuristic (default: single-wave long-K problems only), 0 never, 1 whenever legal
+std::atomic<unsigned long long*> g_timeline{nullptr};
+Knob g_tma_store{1};     // staged epilogue uses TMA bulk stores when it can (pq_debug_set_tma_store)
+Knob g_multi_tma{1};     // multi-destination (NVLink) epilogues hand their tiles to TMA stores (pq_debug_set_multi_tma)
+Knob g_sk_mode{-1};  // -1 heuristic (default: single-wave long-K problems only), 0 never, 1 whenever legal
 
 bool sk_alloc_slot(SkPool& pool, int num_sms) {
   if (pool.count >= SK_MAX_SLOTS) return false;
@@ -846,45 +897,50 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   rc = make_tmap(&tb, b, g.N, g.K, ldb, L::B_ROWS / MC);
   if (rc) return rc;
 
-  CUtensorMap ty;
+  typename YMap<STAGED>::type ty;
   memset(&ty, 0, sizeof(ty));
   g.tma_store = 0;
-  if (STAGED && g.n_out == 1 && g.vec_ok && g_tma_store) {
-    // output as [M rows] x [N elements], boxes of 128 bytes x 128 rows, same 128B swizzle as the staging tile
+  const bool tma_ok = g.vec_ok && g_tma_store.load(std::memory_order_relaxed) != 0;
+  if constexpr (STAGED) {
+    // output(s) as [M rows] x [N elements], boxes of 128 bytes x 128 rows, same 128B swizzle as the staging tile.
+    // One map per destination: the local buffer and (fused all-gather / reduce-scatter) the peers' buffers, which
+    // TMA writes over NVLink in full lines.  A reduce-scatter destination is an [M, scatter_cols] matrix of its own.
     constexpr int esz = (int)sizeof(OutT);
-    auto fn = get_encode_fn();
-    if (!fn) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
-    cuuint64_t strides[1] = {(cuuint64_t)(g.ldo * esz)};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)BLOCK_M};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&ty, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, g.out[0], dims,
-                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS) g.tma_store = 1;
-  } else if (L::WS_NBUF > 0 && g.n_out == 1 && g.vec_ok && g_tma_store) {
+    constexpr int subc = 128 / esz;
+    const bool multi = g.n_out > 1 || g.scatter_cols > 0;
+    const bool want = tma_ok && !g.multimem && (!multi || g_multi_tma.load(std::memory_order_relaxed) != 0) &&
+                      (g.scatter_cols == 0 || g.scatter_cols % subc == 0);
+    if (want) {
+      bool ok = true;
+      for (int d = 0; d < g.n_out && ok; ++d) {
+        uint64_t cols = (uint64_t)g.N;
+        if (g.scatter_cols > 0) {
+          const long long left = (long long)g.N - (long long)d * g.scatter_cols;
+          if (left <= 0) { ty.m[d] = ty.m[0]; continue; }      // destination past the last column: never addressed
+          cols = (uint64_t)(left < g.scatter_cols ? left : g.scatter_cols);
+        }
+        ok = encode_tmap_2d(&ty.m[d], g.out[d], esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                            cols, (uint64_t)g.M, (uint64_t)(g.ldo * esz), (uint32_t)subc, (uint32_t)BLOCK_M,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE) == PQ_OK;
+      }
+      if (ok) g.tma_store = 1;
+    }
+  } else if (L::WS_NBUF > 0 && g.n_out == 1 && tma_ok) {
     // per-warp epilogue boxes: [32 rows] x [32 columns]; 64B swizzle for 16-bit outputs, 128B swizzle for fp32
     constexpr int esz = (int)sizeof(OutT);
-    auto fn = get_encode_fn();
-    if (!fn) PQ_FAIL(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
-    cuuint64_t strides[1] = {(cuuint64_t)(g.ldo * esz)};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&ty, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, g.out[0], dims,
-                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    esz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS) g.tma_store = 1;
+    if (encode_tmap_2d(&ty, g.out[0], esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                       (uint64_t)g.N, (uint64_t)g.M, (uint64_t)(g.ldo * esz), 32, 32,
+                       esz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE) == PQ_OK)
+      g.tma_store = 1;
   }
   auto kern = qgemm_kernel<CG, BN, STAGES, OutT, STAGED, MC>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  static int max_clusters = 0;   // co-resident clusters of this kernel (matters for 4-CTA clusters: 33, not 37)
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
-    max_clusters = num_sms / (CG * MC);
-    if (attr_err == cudaSuccess && MC > 1) {
+  static PerDeviceOnce once;   // function attributes are per device: set them on every device this process drives
+  int max_clusters = 0;        // co-resident clusters of this kernel (matters for 4-CTA clusters: 33, not 37)
+  const cudaError_t attr_err = once.run([&](int* value) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    *value = num_sms / (CG * MC);
+    if (e == cudaSuccess && MC > 1) {
       cudaLaunchConfig_t oc = {};
       oc.gridDim = dim3((unsigned)(num_sms / (CG * MC) * (CG * MC)), 1, 1);
       oc.blockDim = dim3(NUM_THREADS, 1, 1);
@@ -897,10 +953,11 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
       oc.attrs = oa;
       oc.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &oc) == cudaSuccess && n > 0) max_clusters = n;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &oc) == cudaSuccess && n > 0) *value = n;
       else (void)cudaGetLastError();
     }
-  });
+    return e;
+  }, &max_clusters);
   if (attr_err != cudaSuccess)
     PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));
 
@@ -913,13 +970,13 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
     const long long units = tiles * g.num_k_blocks;
     const long long waves = (tiles + W - 1) / W;
     const double eff = (double)tiles / (double)(waves * W);
-    // Heuristic (mode -1, default): stream-K pays only when the whole problem is less than one wave of
-    // tiles and K is long -- each worker then streams K/S of a tile and the int32 fix-up (one partial
-    // write + read per worker) is small next to it.  Measured (profiles/README_r1.md): 128x1024x16384
-    // 27.7 -> 15.4 us, 128x4096x11008 20.0 -> 17.1 us, but 128x4096x4096 9.6 -> 12.5 us and
-    // 2048x4096x4096 29.2 -> 35.9 us, hence K >= 8192 and a single wave.
+    // Heuristic (mode -1, default): stream-K pays only when the whole problem keeps at most HALF of the workers
+    // busy with whole tiles and K is long (>= 8192) -- each worker then streams K/S of a tile and the int32 fix-up
+    // (one partial write + read per worker) is small next to it.  Measured (gpurun_out/sweep_tune_r2.csv, round 2):
+    // 128x1024x16384 29.1 -> 17.7 us, 256x2048x16384 26.5 -> 20.3 us, 256x1024x8192 14.9 -> 13.9 us; with more than
+    // half a wave of tiles the fix-up traffic loses: 1024x4096x8192 25.1 -> 36.5 us, 512x8192x8192 26.0 -> 36.4 us.
     (void)eff;
-    bool want = !STAGED && MC == 1 && ((g_sk_mode == 1) || (g_sk_mode < 0 && waves == 1 && tiles < W && g.num_k_blocks >= 64));
+    bool want = !STAGED && MC == 1 && ((g_sk_mode == 1) || (g_sk_mode < 0 && waves == 1 && tiles * 2 <= W && g.num_k_blocks >= 64));
     long long w_sk = W;
     if (units / 4 < w_sk) w_sk = units / 4;     // at least ~4 K blocks per worker
     if (w_sk < 2 || tiles % w_sk == 0) want = false;
@@ -954,11 +1011,11 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   return PQ_OK;
 }
 
-int g_force_cfg = -1;  // test hook: see pq_debug_set_gemm_config
-int g_force_staged = 0;  // test hook: staged epilogue even for a single destination
-int g_epi_dbg = 0;       // profiling only: see GemmArgs::dbg
-int g_narrow_tiles = 1;  // heuristic may pick BLOCK_N in {240, 224, 208} (pq_debug_set_narrow_tiles)
-int g_prefetch_b = 0;    // L2 prefetch of the weight operand (pq_debug_set_prefetch): measured SLOWER, off
+Knob g_force_cfg{-1};  // test hook: see pq_debug_set_gemm_config
+Knob g_force_staged{0};  // test hook: staged epilogue even for a single destination
+Knob g_epi_dbg{0};       // profiling only: see GemmArgs::dbg
+Knob g_narrow_tiles{1};  // heuristic may pick BLOCK_N in {240, 224, 208} (pq_debug_set_narrow_tiles)
+Knob g_prefetch_b{0};    // L2 prefetch of the weight operand (pq_debug_set_prefetch): measured SLOWER, off
 
 template <typename OutT>
 int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const GemmArgs& g,
@@ -981,10 +1038,21 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
     //    operand bytes per MMA) but ~1 us more fixed cost, so it needs enough K blocks per worker.
     const long long m128 = (g.M + 127) / 128;
     const long long t0 = m128 * ((g.N + 255) / 256), t2 = m128 * ((g.N + 127) / 128), t3 = m128 * ((g.N + 63) / 64);
-    if (t3 <= num_sms) cfg = 3;
-    else if (t2 <= num_sms) cfg = 2;
+    const long long kb_all = (g.K + BLOCK_K - 1) / BLOCK_K;
+    const long long t4 = (long long)((g.M + 255) / 256) * ((g.N + 127) / 128);   // 256x128 pair tiles
+    // One-wave regime (gpurun_out/sweep_tune_r2.csv): the smallest tile shape that still fits one wave wins; for long
+    // K (>= 8192) and at least one full pair of row blocks the CTA-pair shapes win (64 instead of 96 operand bytes
+    // per SM-cycle): 512x4096x8192 17.1 (256x128 pairs) vs 17.9 us (128x128); 512x8192x8192 26.0 (256x256 pairs) vs
+    // 29.8 us (128x256); 256x16384x16384 56.8 vs 65.6 us.
+    const bool long_k_pairs = kb_all >= 64 && g.M >= 256;
+    if (t3 <= num_sms) {
+      cfg = 3;
+      // very long K, few tiles: 256x128 pair tiles + stream-K (1024x1024x16384: 23.2 vs 27.6 us)
+      if (kb_all >= 128 && g.M >= 256 && t4 * 2 <= num_sms / 2) cfg = 4;
+    }
+    else if (t2 <= num_sms) cfg = long_k_pairs ? 4 : 2;
     else if (t0 <= num_sms) {
-      cfg = 0;
+      cfg = long_k_pairs ? 1 : 0;
       // one short-K wave: the epilogue is the kernel.  16-bit outputs already leave through per-warp TMA
       // stores (faster still: 4096x3072x768 12.9 us vs 14.5 us), fp32 outputs take the CTA-staged TMA path.
       if constexpr (std::is_same<OutT, float>::value) {
@@ -992,27 +1060,29 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
           return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
       }
     } else {
-      const long long t1 = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
-      const long long pairs = num_sms / 2;
-      const long long w0 = (t0 + num_sms - 1) / num_sms, w1 = (t1 + pairs - 1) / pairs;
-      const double eff0 = (double)t0 / (double)(w0 * num_sms), eff1 = (double)t1 / (double)(w1 * pairs);
-      const long long kb = (g.K + BLOCK_K - 1) / BLOCK_K;
-      cfg = (eff1 + 0.03 >= eff0 && w1 * kb > 80) ? 1 : 0;
-      // Narrower tiles (BLOCK_N = 240 / 224 / 208) when they cut the ragged last wave: the main loop
-      // of a worker lasts waves x BLOCK_N column-units, e.g. 2048 x 4096: 2 x 256 -> 2 x 240, and
-      // 2048 x 11008: 5 x 256 -> 5 x 240 (99 % of the SM-columns busy).  A narrower tile loads ~3 %
-      // more operand bytes per MMA, so it has to win by more than that.
-      if (g_narrow_tiles) {
-        const int cg = cfg == 1 ? 2 : 1;
+      // More than one wave of 128x256 tiles.  Per-worker cost model: waves x BLOCK_N column-units, with a
+      // penalty for 1-CTA tiles.  Since the MMA issue loop was fixed (round 2: one elected lane inside uniform
+      // control flow) the CTA pair is the faster steady state -- half of the weight tile per SM, 64 instead of
+      // 96 operand bytes per SM-cycle: 2048x11008x4096 59.2 us vs 67.4 us, 8192^3 323 vs 377 us -- so 1-CTA
+      // tiles are taken only when their wave quantisation is better by more than that (or M <= 128).
+      // Narrower tiles (BLOCK_N = 240 / 224 / 208) cut the ragged last wave, e.g. 2048 x 4096: 2 x 256 -> 2 x 240
+      // and 2048 x 12288: 6 x 256 -> 6 x 224 column-units per worker; a narrower tile loads ~3 % more operand
+      // bytes per MMA, so it has to win by more than that.
+      static const int bns[4] = {256, 240, 224, 208};
+      static const int cfg_pair[4] = {1, 8, 9, 10}, cfg_single[4] = {0, 11, 12, 13};
+      double best = 1e30;
+      for (int cg = 2; cg >= 1; --cg) {
+        if (cg == 2 && g.M <= 128) continue;
         const long long mt = (g.M + 128 * cg - 1) / (128 * cg), W = num_sms / cg;
-        const long long base = ((mt * ((g.N + 255) / 256) + W - 1) / W) * 256;
-        long long best = base * 97 / 100;
-        static const int bns[3] = {240, 224, 208};
-        for (int i = 0; i < 3; ++i) {
-          const long long cost = ((mt * ((g.N + bns[i] - 1) / bns[i]) + W - 1) / W) * bns[i];
-          if (cost < best) { best = cost; cfg = (cg == 2 ? 8 : 11) + i; }
+        for (int i = 0; i < (g_narrow_tiles ? 4 : 1); ++i) {
+          const long long nt = (g.N + bns[i] - 1) / bns[i];
+          double cost = (double)(((mt * nt + W - 1) / W) * bns[i]);
+          if (i > 0) cost *= 1.03;
+          if (cg == 1) cost *= 1.12;
+          if (cost < best) { best = cost; cfg = cg == 2 ? cfg_pair[i] : cfg_single[i]; }
         }
       }
+      const long long kb = (g.K + BLOCK_K - 1) / BLOCK_K;
       // Short-K, multi-wave problems are bound by the output write, not by the MMAs: the staged
       // epilogue (whole 256-byte row segments per store) is 9-14 % faster there (K <= 2048:
       // 4096x3072x768 21.0 -> 18.0 us, 8192x8192x1024 75.2 -> 68.9 us) and slower for long K.
@@ -1082,7 +1152,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
     g.out[d] = outs[d];
     if ((uintptr_t)outs[d] & 15) g.vec_ok = 0;
   }
-  g.tl = g_timeline;
+  g.tl = g_timeline.load(std::memory_order_relaxed);
   g.prefetch_b = g_prefetch_b;
   g.dbg = g_epi_dbg;
   g.scatter_cols = (int)scatter_cols;
@@ -1131,5 +1201,6 @@ extern "C" void pq_debug_set_epilogue(int bits) { pq::g_epi_dbg = bits; }
 extern "C" void pq_debug_set_narrow_tiles(int on) { pq::g_narrow_tiles = on; }
 extern "C" void pq_debug_set_prefetch(int on) { pq::g_prefetch_b = on; }
 extern "C" void pq_debug_set_tma_store(int on) { pq::g_tma_store = on; }
-// device buffer of 32 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
-extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline = dev_buf; }
+// device buffer of 40 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
+extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline.store(dev_buf, std::memory_order_relaxed); }
+extern "C" void pq_debug_set_multi_tma(int on) { pq::g_multi_tma = on; }

@@ -26,8 +26,8 @@
 #include <type_traits>
 
 namespace pq {
-int g_force_tpr = 0, g_force_vpt = 0;   // test hook (pq_debug_set_quant_config)
-int g_weight_prefetch = 1;              // pq_qlinear: the act-quant kernel pulls the weights into L2
+Knob g_force_tpr{0}, g_force_vpt{0};   // test hook (pq_debug_set_quant_config)
+Knob g_weight_prefetch{1};              // pq_qlinear: the act-quant kernel pulls the weights into L2
 namespace {
 
 using namespace qmath;
