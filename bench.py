@@ -3,21 +3,25 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (config.workload = "llama7b_linears_2048tok", BASELINE.json configs[2]): one "step"
-pushes one batch of 2048 synthetic bf16 tokens through the seven linears of a Llama-7B block
-(q,k,v,o: 4096->4096; gate,up: 4096->11008; down: 11008->4096), each as a dynamic-quant linear
-forward = per-token act-quant kernel + tcgen05 int8 GEMM with the fused dequant epilogue
-(14 kernel launches / step, random-init weights quantised once at load).
-
-  value   whole-job int8 TOPS = n_gpus * 2*M*sum(N*K) / step time, inputs resident in HBM.
-  e2e     same metric with HOST buffers: every step copies the four activation tensors from
-          pinned host memory and brings the seven outputs back (copies inside the timed region).
-  N > 1   rows (tokens) are independent, so the path shards by tokens with no collective: every
-          rank runs the same step on its own 2048-token batch (weak scaling).  The column-
-          parallel Llama-70B linear with its NCCL all-gather (the path's one exchange step)
-          is timed beside it and reported under "sharded_70b".
-  --impl reference   times the oracle's CPU path (the reference checkout is absent, so the
-          restatement stands in: oracle/protoquant_oracle.py) on all host threads.
+N = 1 -- workload "llama7b_linears_2048tok" (BASELINE.json configs[2]): one "step" pushes one batch of 2048
+  synthetic bf16 tokens through the seven linears of a Llama-7B block (q,k,v,o: 4096->4096; gate,up: 4096->11008;
+  down: 11008->4096) the way `swap_linear` sets a block up: every DISTINCT activation is quantised once
+  (x_attn for q/k/v, attn_out for o, x_mlp for gate/up, h_mlp for down) and linears that share an input run as one
+  GEMM over their concatenated per-channel-quantised weights -- 4 act-quant launches + 4 tcgen05 GEMM launches with
+  the fused dequant epilogue, outputs bit-identical to seven separate linears (tests/test_gpu_module.py).
+    value   whole-job int8 TOPS = 2*M*sum(N*K) / step time, inputs resident in HBM, CUDA-graph replay.
+    e2e     same metric through the public module API with HOST buffers: every step copies the four activation
+            tensors from pinned host memory and brings the seven outputs back (copies inside the timed region).
+    roofline  the tcgen05 GEMM (dominant kernel) against 2 x the measured cuBLAS bf16 peak, next to cuBLASLt int8
+            (torch._int_mm) on the same shapes in the same run; act-quant against the measured HBM peak.
+N > 1 -- workload "llama70b_up_proj_colsharded_2048tok" (BASELINE.json configs[3], north_star (4)): the Llama-70B
+  up projection 8192 -> 28672 column-sharded over the N GPUs, 2048 tokens, all-gather of the output slices
+  INCLUDED (fused into the GEMM epilogue: TMA stores into every rank's symmetric output buffer over NVLink,
+  one cross-rank barrier).  Total work is fixed -> "scaling": "strong".  value = 2*M*N*K / time (max over ranks);
+  roofline.bound = "nvlink": bytes every rank must receive / time against the measured 770 GB/s peer bandwidth.
+  The sharded output is compared bit for bit with the replicated layer on every rank; a mismatch fails the run.
+--impl reference   times the oracle's CPU path (the reference checkout is absent, so the restatement stands in:
+  oracle/protoquant_oracle.py) on all host threads, same workload and token count as N = 1.
 """
 import argparse
 import json
@@ -36,6 +40,11 @@ LINEARS = [  # name, K (in), N (out), which activation buffer feeds it
     ("down_proj", 11008, 4096, "h_mlp"),
 ]
 ACTS = {"x_attn": 4096, "attn_out": 4096, "x_mlp": 4096, "h_mlp": 11008}
+# how swap_linear(fuse_shared_inputs=True) groups them: one act-quant + one GEMM per distinct activation
+GROUPS = [("qkv_proj", ("q_proj", "k_proj", "v_proj"), "x_attn"), ("o_proj", ("o_proj",), "attn_out"),
+          ("gate_up_proj", ("gate_proj", "up_proj"), "x_mlp"), ("down_proj", ("down_proj",), "h_mlp")]
+NVLINK_PEER_GBS = 770.0   # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)
+S70_K, S70_N, S70_M = 8192, 28672, 2048
 OPS_PER_STEP = sum(2 * M_TOKENS * n * k for _, k, n, _ in LINEARS)
 NOMINAL_INT8_TOPS = 4500.0
 
@@ -104,8 +113,9 @@ def dist_env():
 
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """CPU baseline arm: the oracle's torch-threaded restatement of the same step (kind = "port":
-    /root/reference holds no sources to compile or import)."""
+    """CPU baseline arm: the oracle's torch-threaded restatement of the same workload as our arm at this --gpus
+    (kind = "port": /root/reference holds no sources to compile or import).  N = 1: the 2048-token
+    Llama-7B step; N > 1: the Llama-70B up projection at 2048 tokens (rank 0 alone runs it)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
@@ -115,14 +125,29 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    # bounded sample: the full 7-linear step on a 256-token slice of the 2048-token batch
-    m_sample = 256
-    layers = []
-    for name, k, n, src in LINEARS:
-        w = (torch.rand(n, k) * 2 - 1) / k ** 0.5
-        wq, sw = O.quantize_rowwise(w)
-        layers.append((torch.from_numpy(wq).t(), torch.from_numpy(sw), torch.randn(n), src))
-    acts = {a: torch.randn(m_sample, k).to(torch.bfloat16) for a, k in ACTS.items()}
+    g = torch.Generator().manual_seed(0)
+    if args.gpus > 1:
+        workload, m_sample = "llama70b_up_proj_colsharded_2048tok", S70_M
+        wq = torch.randint(-127, 128, (S70_N, S70_K), dtype=torch.int8, generator=g)
+        layers = [(wq.t(), torch.rand(S70_N, generator=g) * 1e-3, None, "x")]
+        acts = {"x": torch.randn(m_sample, S70_K, generator=g).to(torch.bfloat16)}
+        ops = 2.0 * m_sample * S70_N * S70_K
+        cfg = {"workload": workload, "tokens": m_sample, "layer": [S70_K, S70_N], "act_dtype": "bf16", "out_dtype": "bf16"}
+        what = "the Llama-70B up projection (8192 -> 28672) on 2048 tokens"
+        scaling = "strong"
+    else:
+        workload, m_sample = "llama7b_linears_2048tok", M_TOKENS
+        layers = []
+        for name, k, n, src in LINEARS:
+            w = (torch.rand(n, k, generator=g) * 2 - 1) / k ** 0.5
+            wq, sw = O.quantize_rowwise(w)
+            layers.append((torch.from_numpy(wq).t(), torch.from_numpy(sw), torch.randn(n, generator=g), src))
+        acts = {a: torch.randn(m_sample, k, generator=g).to(torch.bfloat16) for a, k in ACTS.items()}
+        ops = float(OPS_PER_STEP)
+        cfg = {"workload": workload, "tokens_per_gpu": m_sample, "act_dtype": "bf16", "out_dtype": "bf16",
+               "linears": {l[0]: [l[1], l[2]] for l in LINEARS}}
+        what = "the full 2048-token step, all 7 linears"
+        scaling = "weak"
 
     def step():
         for wq_t, sw, b, src in layers:
@@ -130,20 +155,21 @@ def run_reference(args):
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
-    steps = max(1, min(args.steps, 20))
+    t_probe = time.perf_counter()
+    step()
+    t_probe = time.perf_counter() - t_probe
+    steps = max(1, min(args.steps, 20, int(60.0 / max(t_probe, 1e-3))))    # keep the whole arm within about a minute
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    ops = OPS_PER_STEP * m_sample / M_TOKENS
     tops = ops / dt / 1e12
-    sample = f"{m_sample}-token slice of the 2048-token step, all 7 linears, {steps} steps"
+    sample = f"{what}, {steps} steps, torch CPU _int_mm on {cores} threads"
     line = {
         "impl": "reference", "metric": "int8_qlinear_tops", "value": tops, "unit": "TOPS", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": "llama7b_linears_2048tok", "tokens": m_sample, "linears": [l[0] for l in LINEARS]},
-        "tokens_per_s": m_sample / dt,
+        "scaling": scaling, "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": cfg, "tokens_per_s": m_sample / dt,
         "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,7 +185,7 @@ def cpu_baseline_leg(budget_s=12.0):
     import protoquant_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    m_sample = 256
+    m_sample = M_TOKENS
     g = torch.Generator().manual_seed(0)
     layers = []
     for name, k, n, src in LINEARS:
@@ -176,16 +202,51 @@ def cpu_baseline_leg(budget_s=12.0):
     while True:
         step()
         n += 1
-        if time.perf_counter() - t0 > budget_s or n >= 20:
+        if time.perf_counter() - t0 > budget_s or n >= 10:
             break
     dt = (time.perf_counter() - t0) / n
     tops = OPS_PER_STEP * m_sample / M_TOKENS / dt / 1e12
     return {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port",
-            "sample": f"{m_sample}-token slice of the 2048-token step, all 7 linears, {n} steps, torch CPU _int_mm",
+            "sample": f"the full {m_sample}-token step, all 7 linears, {n} steps, torch CPU _int_mm on {cores} threads",
             "tokens_per_s": m_sample / dt}
 
 
 # ------------------------------------------------------------------------------ our arm
+def capture(torch, dev, fn, no_graph=False):
+    """Warm `fn` on a side stream and capture it into a CUDA graph; returns (callable, launch mode)."""
+    fn()
+    if no_graph:
+        return fn, "eager"
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        return graph.replay, "cuda_graph_replay"
+    except Exception as ex:  # capture unsupported: stay eager
+        sys.stderr.write(f"bench: CUDA graph capture failed ({ex!r}); running eager\n")
+        torch.cuda.synchronize()
+        return fn, "eager"
+
+
+def timed(torch, run, reps, warm=3):
+    """CUDA-event time (ms) of `reps` calls of `run` on the current stream, after `warm` untimed calls."""
+    for _ in range(warm):
+        run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -200,58 +261,80 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    ctx = {"torch": torch, "dist": dist, "pq": pq, "F": F, "rank": rank, "world": world, "local": local, "dev": dev,
+           "peaks": peaks, "args": args}
+    rc = run_sharded(ctx) if world > 1 else run_single(ctx)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return rc
+
+
+class Llama7BBlockLinears:
+    """The seven linears of a Llama-7B block, random-init, converted with the public swap helper."""
+
+    def __init__(self, torch, pq, dev):
+        from torch import nn
+
+        class Block(nn.Module):
+            def __init__(self):
+                super().__init__()
+                for name, k, n, _ in LINEARS:
+                    setattr(self, name, nn.Linear(k, n, bias=True))
+
+        blk = Block().to(torch.bfloat16).to(dev)
+        self.block = pq.swap_linear(blk)      # fuse_shared_inputs=True: q/k/v and gate/up become one GEMM each
+        b = self.block
+        assert isinstance(b.q_proj, pq.SharedInputLinear) and isinstance(b.gate_proj, pq.SharedInputLinear)
+        self.fused = {"qkv_proj": b.q_proj.fused, "o_proj": b.o_proj, "gate_up_proj": b.gate_proj.fused, "down_proj": b.down_proj}
+
+
+def run_single(ctx):
+    torch, pq, F, dev, peaks, args = ctx["torch"], ctx["pq"], ctx["F"], ctx["dev"], ctx["peaks"], ctx["args"]
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
     torch.manual_seed(1234 + rank)
 
-    # ---- load-time: random-init weights of the named architecture, quantised once ----
-    mods = {}
-    for name, k, n, src in LINEARS:
-        lin = torch.nn.Linear(k, n, bias=True).to(torch.bfloat16).to(dev)
-        mods[name] = pq.DynamicQuantLinear.from_float(lin)
-        del lin
+    # ---- load-time: random-init weights of the named architecture, quantised once (public swap helper) ----
+    blk = Llama7BBlockLinears(torch, pq, dev)
+    fused = blk.fused
     acts = {a: torch.randn(M_TOKENS, k, device=dev).to(torch.bfloat16) for a, k in ACTS.items()}
     xq_ws = {a: (F.alloc_q(M_TOKENS, k, dev), torch.empty(M_TOKENS, dtype=torch.float32, device=dev)) for a, k in ACTS.items()}
-    outs = {name: torch.empty(M_TOKENS, n, dtype=torch.bfloat16, device=dev) for name, k, n, _ in LINEARS}
-
-    def linear_fwd(name, src):
-        # the module's own forward path (one pq_qlinear call = act-quant launch + GEMM launch) on
-        # preallocated buffers, so that the step can be captured into a CUDA graph
-        m = mods[name]
-        F.qlinear_into(acts[src], m.qweight_storage, m.in_features, m.weight_scale, m.bias, outs[name], *xq_ws[src])
+    outs = {g: torch.empty(M_TOKENS, fused[g].out_features, dtype=torch.bfloat16, device=dev) for g, _, _ in GROUPS}
 
     def step():
+        # one pq_qlinear call (act-quant launch + GEMM launch) per distinct activation, on preallocated buffers so
+        # that the step can be captured into a CUDA graph: exactly what the modules' forward does
+        for g, members, src in GROUPS:
+            m = fused[g]
+            F.qlinear_into(acts[src], m.qweight_storage, m.in_features, m.weight_scale, m.bias, outs[g], *xq_ws[src])
+
+    # round 1's step for comparison: one act-quant + one GEMM per linear (7 + 7 launches) on row slices of the same weights
+    outs7 = {name: torch.empty(M_TOKENS, n, dtype=torch.bfloat16, device=dev) for name, k, n, _ in LINEARS}
+    slices7 = {}
+    for g, members, src in GROUPS:
+        lo = 0
+        for name in members:
+            n = outs7[name].shape[1]
+            m = fused[g]
+            slices7[name] = (m.qweight_storage[lo:lo + n], m.in_features, m.weight_scale[lo:lo + n],
+                             m.bias[lo:lo + n] if m.bias is not None else None, src)
+            lo += n
+
+    def step_unfused():
         for name, k, n, src in LINEARS:
-            linear_fwd(name, src)
+            wq, kf, sw, b, _ = slices7[name]
+            F.qlinear_into(acts[src], wq, kf, sw, b, outs7[name], *xq_ws[src])
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-
-    # The step is launch-bound-ish from Python (14 ctypes calls of ~15 us each), so it is captured
-    # once into a CUDA graph and replayed: same 14 kernels, same buffers, no host work per launch.
     launches_per_step = pq.launch_count()
     step()
     launches_per_step = pq.launch_count() - launches_per_step
-    run_step, launch_mode = step, "eager"
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            run_step, launch_mode = graph.replay, "cuda_graph_replay"
-        except Exception as ex:  # capture unsupported: stay eager
-            sys.stderr.write(f"bench: CUDA graph capture failed ({ex!r}); running eager\n")
-            torch.cuda.synchronize()
+    run_step, launch_mode = capture(torch, dev, step, args.no_graph)
     for _ in range(max(args.warmup, 3)):
         run_step()
     barrier()
@@ -278,63 +361,48 @@ def run_ours(args):
         except Exception:
             pass
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    ms_per_step = ms / args.steps
-    value = world * OPS_PER_STEP / (ms_per_step * 1e-3) / 1e12
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    value = OPS_PER_STEP / (ms_per_step * 1e-3) / 1e12
+    clk_now = sampler.result()
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM) ----
-    # Average launch duration = CUDA-event time of a graph that replays ONLY the step's seven GEMM
-    # launches (same weights cycling through 202 MB, pre-quantised activations), divided by the
-    # launch count; a second graph does the same for the seven act-quant launches.  (Bracketing every
-    # launch with its own pair of events inflates a 30-70 us kernel by ~10 us of event latency.)
-    for name, k, n, src in LINEARS:
+    # Average launch duration = CUDA-event time of a graph that replays ONLY the step's GEMM launches (same weights
+    # cycling through 202 MB, pre-quantised activations), divided by the launch count; further graphs do the same
+    # for cuBLASLt int8 (torch._int_mm: int32 output, no epilogue) on the same shapes and for the act-quant launches.
+    # (Bracketing every launch with its own pair of events inflates a 30-130 us kernel by ~10 us of event latency.)
+    for g, members, src in GROUPS:
         F.quantize_act(acts[src], out=xq_ws[src])
 
     def gemm_only():
-        for name, k, n, src in LINEARS:
-            m = mods[name]
-            F.qgemm(xq_ws[src][0], xq_ws[src][1], m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
+        for g, members, src in GROUPS:
+            m = fused[g]
+            F.qgemm(xq_ws[src][0], xq_ws[src][1], m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[g])
 
     def quant_only():
-        for name, k, n, src in LINEARS:
+        for g, members, src in GROUPS:
             F.quantize_act(acts[src], out=xq_ws[src])
 
-    def time_graph(fn, reps):
-        fn()
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            fn()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        run = fn
-        if not args.no_graph:
-            try:
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
-                    fn()
-                run = gr.replay
-            except Exception:
-                torch.cuda.synchronize()
-        for _ in range(3):
-            run()
-        t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_a.record()
-        for _ in range(reps):
-            run()
-        t_b.record()
-        torch.cuda.synchronize()
-        return t_a.elapsed_time(t_b)
+    wts = {g: fused[g].qweight.t() for g, _, _ in GROUPS}      # [K, N] column-major views: what _int_mm wants
+    acc32 = {g: torch.empty(M_TOKENS, fused[g].out_features, dtype=torch.int32, device=dev) for g, _, _ in GROUPS}
+
+    def cublaslt_only():
+        for g, members, src in GROUPS:
+            torch._int_mm(xq_ws[src][0], wts[g], out=acc32[g])
 
     roof_steps = max(3, min(args.steps, 100))
-    gemm_ms = time_graph(gemm_only, roof_steps)
-    quant_ms = time_graph(quant_only, roof_steps)
-    quant_bytes = roof_steps * sum(M_TOKENS * (3 * k + 4) for _, k, n, _ in LINEARS)
+    gemm_ms = timed(torch, capture(torch, dev, gemm_only, args.no_graph)[0], roof_steps)
+    quant_ms = timed(torch, capture(torch, dev, quant_only, args.no_graph)[0], roof_steps)
+    try:
+        cublas_ms = timed(torch, capture(torch, dev, cublaslt_only, args.no_graph)[0], roof_steps)
+    except Exception as ex:
+        sys.stderr.write(f"bench: cuBLASLt int8 comparator unavailable ({ex!r})\n")
+        cublas_ms = None
+    del acc32
+    unfused_ms = timed(torch, capture(torch, dev, step_unfused, args.no_graph)[0], roof_steps) / roof_steps
+    n_gemm = len(GROUPS)
+    quant_bytes = roof_steps * sum(M_TOKENS * (3 * k + 4) for k in ACTS.values())
     gemm_tops = OPS_PER_STEP * roof_steps / (gemm_ms * 1e-3) / 1e12
+    cublas_tops = OPS_PER_STEP * roof_steps / (cublas_ms * 1e-3) / 1e12 if cublas_ms else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -344,47 +412,53 @@ def run_ours(args):
             traffic = None
     # Which measured peak applies: the burst figure for kernels timed alone at full clocks, the sustained one when
     # the timed region ran under the power cap (SM clock well below max or sw_power_cap seen by the sampler).
-    clk_now = sampler.result()
     capped = ("sw_power_cap" in clk_now["reasons"]) or bool(
         clk_now["sm_mhz"] and clk_now["sm_max_mhz"] and clk_now["sm_mhz"] < 0.93 * clk_now["sm_max_mhz"])
     peak_burst, peak_sust = 2.0 * peaks["bf16_tflops"], 2.0 * peaks["bf16_tflops_sustained"]
     peak_tops = peak_sust if capped else peak_burst
+    act_gbs = quant_bytes / (quant_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "tensor", "kernel": "qgemm_kernel (tcgen05.mma.kind::i8)", "achieved": gemm_tops, "peak": peak_tops,
+        "bound": "tensor", "kernel": "qgemm_kernel (tcgen05.mma.kind::i8, cta_group::2)", "achieved": gemm_tops, "peak": peak_tops,
         "unit": "TFLOP/s", "frac": gemm_tops / peak_tops, "traffic": traffic,
         "peak_regime": "sustained (power-capped run)" if capped else "burst",
         "frac_vs_burst": gemm_tops / peak_burst, "frac_vs_sustained": gemm_tops / peak_sust,
+        "frac_of_nominal_int8": gemm_tops / NOMINAL_INT8_TOPS,
+        "cublaslt_int8_tops": cublas_tops, "vs_cublaslt": (gemm_tops / cublas_tops) if cublas_tops else None,
+        "cublaslt_note": "torch._int_mm (cuBLASLt int8, int32 output, no dequant epilogue) on the same 4 GEMM shapes and operands, "
+                         "CUDA-graph replay, same run",
         "peak_note": f"2 x {peaks['source']} cuBLAS bf16 (int8 tensor rate = 2x bf16): burst {peaks['bf16_tflops']} TF/s, sustained "
-                     f"{peaks['bf16_tflops_sustained']} TF/s; nominal dense int8 {NOMINAL_INT8_TOPS:.0f} TOPS -> frac_of_nominal "
-                     f"{gemm_tops / NOMINAL_INT8_TOPS:.3f}; the GEMM-only graph is timed right after the step loop, so it runs under "
-                     "the 1 kW power cap whenever the step loop did (a few hundred steps): `peak` follows the clock sampler",
-        "avg_launch_ms": gemm_ms / (roof_steps * len(LINEARS)),
-        "act_quant": {"bound": "hbm", "achieved": quant_bytes / (quant_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                      "unit": "GB/s", "frac": quant_bytes / (quant_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                      "avg_launch_ms": quant_ms / (roof_steps * len(LINEARS)),
-                      "note": "the step's seven act-quant launches alone (2048 x 4096 / 11008 bf16, 25-68 MB each): latency bound; see act_quant_stream"},
+                     f"{peaks['bf16_tflops_sustained']} TF/s; nominal dense int8 {NOMINAL_INT8_TOPS:.0f} TOPS; the GEMM-only graph is "
+                     "timed right after the step loop, so it runs under the 1 kW power cap whenever the step loop did: `peak` "
+                     "follows the clock sampler",
+        "gemm_launches_per_step": n_gemm, "avg_launch_ms": gemm_ms / (roof_steps * n_gemm),
+        "act_quant_step_gbs": act_gbs, "act_quant_step_frac": act_gbs / peaks["hbm_gbs"],
+        "act_quant_step_avg_launch_ms": quant_ms / (roof_steps * n_gemm),
+        "act_quant_step_note": "the step's four act-quant launches alone (2048 x 4096 / 11008 bf16, 25-68 MB each): latency bound",
     }
     # HBM-streaming point for the activation quantizer (traffic >> L2): SURVEY.md §8d
-    if rank == 0:
-        Mbig, Kbig = 131072, 4096
-        xb = torch.randn(Mbig, Kbig, device=dev).to(torch.bfloat16)
-        qb, sb = F.alloc_q(Mbig, Kbig, dev), torch.empty(Mbig, dtype=torch.float32, device=dev)
-        for _ in range(3):
-            F.quantize_act(xb, out=(qb, sb))
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(10):
-            F.quantize_act(xb, out=(qb, sb))
-        s1.record()
-        torch.cuda.synchronize()
-        gbs = 10 * Mbig * (3 * Kbig + 4) / (s0.elapsed_time(s1) * 1e-3) / 1e9
-        roofline["act_quant_stream"] = {"bound": "hbm", "shape": [Mbig, Kbig], "dtype": "bf16", "achieved": gbs,
-                                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
-        del xb, qb, sb
+    Mbig, Kbig = 131072, 4096
+    xb = torch.randn(Mbig, Kbig, device=dev).to(torch.bfloat16)
+    qb, sb = F.alloc_q(Mbig, Kbig, dev), torch.empty(Mbig, dtype=torch.float32, device=dev)
+    s_ms = timed(torch, lambda: F.quantize_act(xb, out=(qb, sb)), 10)
+    gbs = 10 * Mbig * (3 * Kbig + 4) / (s_ms * 1e-3) / 1e9
+    roofline["act_quant_stream_gbs"] = gbs
+    roofline["act_quant_stream_frac"] = gbs / peaks["hbm_gbs"]
+    roofline["act_quant_stream_shape"] = [Mbig, Kbig]
+    del xb, qb, sb
+
+    # ---- sustained regime: at least one second of back-to-back steps (the chip reaches its 1 kW power cap) ----
+    sust_steps = int(min(20000, max(200, 1.2 / (ms_per_step * 1e-3))))
+    s2 = ClockSampler(local)
+    s2.start()
+    sust_ms = timed(torch, run_step, sust_steps, warm=0) / sust_steps
+    s2.stop_flag.set()
+    s2.join(timeout=2)
+    sustained = {"value": OPS_PER_STEP / (sust_ms * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": sust_ms, "steps": sust_steps,
+                 "clocks": s2.result()}
 
     # ---- e2e: host buffers, copies inside the timed region, through the public module API ----
     host_in = {a: torch.randn(M_TOKENS, k).to(torch.bfloat16).pin_memory() for a, k in ACTS.items()}
-    host_out = {name: torch.empty(M_TOKENS, n, dtype=torch.bfloat16).pin_memory() for name, k, n, _ in LINEARS}
+    host_out = {g: torch.empty(M_TOKENS, fused[g].out_features, dtype=torch.bfloat16).pin_memory() for g, _, _ in GROUPS}
     h2d_bytes = sum(t.numel() * 2 for t in host_in.values())
     d2h_bytes = sum(t.numel() * 2 for t in host_out.values())
     copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -409,14 +483,14 @@ def run_ours(args):
                 ev = torch.cuda.Event()
                 ev.record(copy_in)
                 ready[a] = ev
-        for name, k, n, src in LINEARS:
+        for g, members, src in GROUPS:
             main.wait_event(ready[src])
-            y = mods[name](acts2[buf][src])                # public API: the nn.Linear replacement
+            y = fused[g](acts2[buf][src])                  # public API: DynamicQuantLinear.forward (the nn.Linear replacement)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(done)
-                host_out[name].copy_(y, non_blocking=True)
+                host_out[g].copy_(y, non_blocking=True)
                 y.record_stream(copy_out)
         ev = torch.cuda.Event()
         ev.record(main)
@@ -439,62 +513,213 @@ def run_ours(args):
     e2e_drain()                                            # t1 is recorded after the last D2H copy has landed
     t1.record()
     barrier()
-    e2e_ms = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
-    e2e_ms_step = e2e_ms / e2e_steps
-    e2e = {"value": world * OPS_PER_STEP / (e2e_ms_step * 1e-3) / 1e12, "unit": "TOPS", "h2d_bytes_per_step": h2d_bytes,
+    e2e_ms_step = t0.elapsed_time(t1) / e2e_steps
+    e2e = {"value": OPS_PER_STEP / (e2e_ms_step * 1e-3) / 1e12, "unit": "TOPS", "h2d_bytes_per_step": h2d_bytes,
            "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_step, "steps": e2e_steps,
-           "tokens_per_s": world * M_TOKENS / (e2e_ms_step * 1e-3)}
+           "tokens_per_s": M_TOKENS / (e2e_ms_step * 1e-3),
+           "pcie_gbs": (h2d_bytes + d2h_bytes) / (e2e_ms_step * 1e-3) / 1e9}
+    del host_in, host_out, acts2
 
-    # ---- column-parallel Llama-70B linear with its all-gather (the path's exchange step) ----
-    sharded = None
+    # ---- side legs ----
+    def leg(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as ex:  # never let a side measurement kill the headline line
+            return {"error": repr(ex)[:200]}
+
+    sharded = leg(sharded_leg, pq, torch, ctx["dist"], dev, rank, world)
+    decode = leg(decode_leg, pq, F, torch, dev, peaks)
+    fusedp = leg(fused_producer_leg, F, torch, dev, peaks)
+    if "error" not in fusedp:
+        fusedp["llama7b_block_fused_2048tok"] = leg(fused_block_leg, F, torch, dev, fused, acts)
+    bert = leg(bert_leg, pq, F, torch, dev)
+    cpu = cpu_baseline_leg()
+    line = {
+        "metric": "int8_qlinear_tops", "value": value, "unit": "TOPS", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": {"workload": "llama7b_linears_2048tok", "tokens_per_gpu": M_TOKENS, "act_dtype": "bf16",
+                   "out_dtype": "bf16", "linears": {l[0]: [l[1], l[2]] for l in LINEARS},
+                   "launches_per_step": launches_per_step,
+                   "fusion": "swap_linear(fuse_shared_inputs=True): one act-quant + one GEMM per distinct activation "
+                             "(qkv, o, gate_up, down); outputs bit-identical to seven separate linears",
+                   "parallelism": "1 GPU", "launch": launch_mode,
+                   "l2": "inputs larger than L2: each step streams 202 MB of int8 weights + 0.27 GB of activations/outputs (> 126 MB L2)"},
+        "tokens_per_s": M_TOKENS / (ms_per_step * 1e-3),
+        "frac_of_nominal_int8": value / NOMINAL_INT8_TOPS,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clk_now, "sustained": sustained,
+        "step_unfused_7x2_launches_ms": unfused_ms, "step_ms": ms_per_step,
+        "gemm_tops": gemm_tops, "cublaslt_int8_tops": cublas_tops, "vs_cublaslt": roofline["vs_cublaslt"],
+        "act_quant_stream_frac": roofline["act_quant_stream_frac"], "act_quant_step_frac": roofline["act_quant_step_frac"],
+        "sharded_70b": sharded, "decode_16tok": decode, "fused_producers": fusedp, "bert_base_4096tok": bert,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_sharded(ctx):
+    """N > 1: the column-sharded Llama-70B up projection with its all-gather as the headline (strong scaling)."""
+    torch, dist, pq, F, dev, peaks, args = ctx["torch"], ctx["dist"], ctx["pq"], ctx["F"], ctx["dev"], ctx["peaks"], ctx["args"]
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
+    K, N, M = S70_K, S70_N, S70_M
+    g = torch.Generator(device=dev).manual_seed(7)            # same seed on every rank: replicated weights and input
+    wq_full = torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev, generator=g)
+    sw_full = torch.rand(N, device=dev, generator=g) * 1e-3
+    x = torch.randn(M, K, device=dev, generator=g).to(torch.bfloat16)
+    full = pq.DynamicQuantLinear(K, N, bias=False, device=dev)
+    full.qweight_storage[:, :K].copy_(wq_full)
+    full.weight_scale.copy_(sw_full)
+    shf = pq.ShardedDynamicQuantLinear(wq_full, sw_full, None, fused=None)
+
+    def allmax(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate: sharded + gathered output == replicated layer, bit for bit, on every rank ----
+    y_ref = full(x)
+    ok = True
+    for _ in range(3):                                        # both halves of the double buffer, and a reuse
+        ok = ok and bool(torch.equal(shf(x), y_ref))
+    bad = allmax(0.0 if ok else 1.0)
+    if bad:
+        if rank == 0:
+            sys.stderr.write("bench: column-sharded output differs from the replicated layer -- failing the run\n")
+        return 3
+    del y_ref
+    barrier()
+
+    # replicated layer on one GPU (the strong-scaling base), timed on every rank
+    rep_run, _ = capture(torch, dev, lambda: full(x), args.no_graph)
+    rep_ms = allmax(timed(torch, rep_run, 20) / 20)
+    barrier()
+
+    # Two forwards per graph: the module double-buffers its symmetric output (a rank may already be storing step
+    # s+1 into a peer while that peer still reads step s), and a captured forward always uses the buffer it was
+    # captured with -- so the graph holds one forward per buffer.
+    def two_steps():
+        shf(x)
+        shf(x)
+
+    for _ in range(max(args.warmup, 3)):
+        two_steps()
+    barrier()
+    launches0 = pq.launch_count()
+    two_steps()
+    launches_per_step = (pq.launch_count() - launches0) // 2
+    barrier()
+    run2, launch_mode = capture(torch, dev, two_steps, args.no_graph)
+    steps = max(2, args.steps + (args.steps & 1))             # even
+    for _ in range(max((args.warmup + 1) // 2, 2)):
+        run2()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps // 2):
+        run2()
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    if not sampler.samples and sampler.nv is not None:
+        for _ in range(50):
+            run2()
+        try:
+            sampler.sample()
+        except Exception:
+            pass
+        torch.cuda.synchronize()
+    ms_per_step = allmax(e0.elapsed_time(e1) / steps)
+    ops = 2.0 * M * N * K
+    value = ops / (ms_per_step * 1e-3) / 1e12
+
+    # NCCL all-gather baseline (same shard GEMM, separate collective + layout copy)
+    sh_nccl = pq.ShardedDynamicQuantLinear(wq_full, sw_full, None, fused=False)
+    nccl_ms = allmax(timed(torch, lambda: sh_nccl(x), 20) / 20)
+    nccl_ok = bool(torch.equal(sh_nccl(x), full(x)))
+    del sh_nccl
+    barrier()
+
+    # ---- roofline: the slower of the shard GEMM at the measured tensor peak and the bytes every rank must receive ----
+    bytes_in = (world - 1) / world * M * N * 2
+    link_ms = bytes_in / (NVLINK_PEER_GBS * 1e9) * 1e3
+    gemm_ideal_ms = ops / world / (2.0 * peaks["bf16_tflops"] * 1e12) * 1e3
+    target_ms = max(link_ms, gemm_ideal_ms)
+    in_gbs = bytes_in / (ms_per_step * 1e-3) / 1e9
+    rank_tops = ops / world / (ms_per_step * 1e-3) / 1e12
+    link_bound = link_ms >= gemm_ideal_ms
+    roofline = {
+        "bound": "nvlink" if link_bound else "tensor",
+        "kernel": "qgemm_kernel (tcgen05 GEMM, epilogue TMA-stores every tile into all ranks' symmetric output buffers over NVLink)",
+        "achieved": in_gbs if link_bound else rank_tops, "peak": NVLINK_PEER_GBS if link_bound else 2.0 * peaks["bf16_tflops"],
+        "unit": "GB/s" if link_bound else "TFLOP/s",
+        "frac": (in_gbs / NVLINK_PEER_GBS) if link_bound else rank_tops / (2.0 * peaks["bf16_tflops"]), "traffic": None,
+        "nvlink_in_gbs_per_rank": in_gbs, "nvlink_frac_of_770": in_gbs / NVLINK_PEER_GBS, "per_rank_tops": rank_tops,
+        "bytes_received_per_rank": bytes_in, "link_floor_ms": link_ms, "shard_gemm_floor_ms": gemm_ideal_ms,
+        "target_ms": target_ms, "frac_of_target": target_ms / ms_per_step,
+        "peak_note": "the bound is the slower of (a) the bytes every rank must receive at 770 GB/s = measured peer-copy bandwidth per "
+                     "direction per GPU (B200_PROFILING.md; nominal 900) and (b) the shard GEMM 2MNK/" + str(world) + " at 2 x measured cuBLAS bf16 "
+                     f"burst ({peaks['bf16_tflops']} TF/s); frac_of_target = that floor / measured time",
+    }
+
+    # ---- e2e: replicated input from pinned host memory on every rank, own output slice back to the host ----
+    lo, hi = shf.lo, shf.hi
+    host_x = x.cpu().pin_memory()
+    host_y = torch.empty(M, hi - lo, dtype=torch.bfloat16).pin_memory()
+    x_dev = torch.empty_like(x)
+
+    def e2e_step():
+        x_dev.copy_(host_x, non_blocking=True)
+        y = shf(x_dev)
+        host_y.copy_(y[:, lo:hi], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 40))
+    e2e_ms = allmax(timed(torch, e2e_step, e2e_steps, warm=0) / e2e_steps)
+    e2e_ok = bool(torch.equal(host_y, full(x)[:, lo:hi].cpu()))
+    e2e = {"value": ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "h2d_bytes_per_step": world * host_x.numel() * 2,
+           "d2h_bytes_per_step": M * N * 2, "ms_per_step": e2e_ms, "steps": e2e_steps, "output_matches": e2e_ok,
+           "note": "every rank copies the replicated activation in (pinned host -> device) and its own column slice of the result out"}
+    del host_x, host_y, x_dev
+
+    # ---- side legs: NCCL vs fused at M = 16 / 2048, row-parallel down projection, gated MLP; tokens-sharded 7B step ----
     try:
         sharded = sharded_leg(pq, torch, dist, dev, rank, world)
-    except Exception as ex:  # never let the side measurement kill the headline line
-        sharded = {"error": repr(ex)[:200]}
-
-    decode = None
-    if rank == 0:
-        try:
-            decode = decode_leg(pq, F, torch, dev, peaks)
-        except Exception as ex:
-            decode = {"error": repr(ex)[:200]}
-    fused = None
-    if rank == 0:
-        try:
-            fused = fused_producer_leg(F, torch, dev, peaks)
-            fused["llama7b_block_fused_2048tok"] = fused_block_leg(F, torch, dev, mods, acts)
-        except Exception as ex:
-            fused = {"error": repr(ex)[:200]}
-    bert = None
-    if rank == 0:
-        try:
-            bert = bert_leg(pq, F, torch, dev)
-        except Exception as ex:
-            bert = {"error": repr(ex)[:200]}
-    cpu = cpu_baseline_leg() if (rank == 0 and world == 1) else None
+    except Exception as ex:
+        sharded = {"error": repr(ex)[:300]}
+    barrier()
     clocks = sampler.result()
     if rank == 0:
         line = {
-            "metric": "int8_qlinear_tops", "value": value, "unit": "TOPS", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "int8_qlinear_tops", "value": value, "unit": "TOPS", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": "llama7b_linears_2048tok", "tokens_per_gpu": M_TOKENS, "act_dtype": "bf16",
-                       "out_dtype": "bf16", "linears": {l[0]: [l[1], l[2]] for l in LINEARS},
-                       "parallelism": f"tokens x{world} (no collective)", "launch": launch_mode,
-                       "l2": "inputs larger than L2: each step streams 202 MB of int8 weights + 0.27 GB of activations/outputs (> 126 MB L2)"},
-            "tokens_per_s": world * M_TOKENS / (ms_per_step * 1e-3),
-            "frac_of_nominal_int8": value / world / NOMINAL_INT8_TOPS,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "sharded_70b": sharded, "decode_16tok": decode, "fused_producers": fused, "bert_base_4096tok": bert,
+            "config": {"workload": "llama70b_up_proj_colsharded_2048tok", "tokens": M, "layer": [K, N], "act_dtype": "bf16",
+                       "out_dtype": "bf16", "launches_per_step": launches_per_step,
+                       "parallelism": f"column-parallel x{world}: act-quant (replicated) + shard GEMM whose epilogue TMA-stores every tile "
+                                      "into all ranks' output buffers over NVLink (fused all-gather) + 1 cross-rank barrier",
+                       "launch": launch_mode,
+                       "l2": "per-rank working set (weight shard + activation + 117 MB gathered output) is larger than L2"},
+            "tokens_per_s": M / (ms_per_step * 1e-3),
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches_per_step * steps),
+            "clocks": clocks,
+            "bit_identical_to_replicated": True, "fused_path_active": bool(shf.fused), "fused_error": shf.fused_error,
+            "replicated_1gpu_ms": rep_ms, "speedup_vs_replicated_1gpu": rep_ms / ms_per_step,
+            "strong_scaling_efficiency": rep_ms / ms_per_step / world,
+            "nccl_allgather_ms": nccl_ms, "nccl_bit_identical": nccl_ok,
+            "sharded_70b": sharded,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     return 0
 
 
@@ -679,95 +904,37 @@ def bert_leg(pq, F, torch, dev):
     return res
 
 
-def fused_block_leg(F, torch, dev, mods, acts):
-    """The same seven GEMMs wired the way a Llama block uses them, with the producer fusions (§8f-2): RMSNorm -> int8
-    once for q/k/v, once for gate/up; silu(gate)*up -> int8 straight from the gate/up outputs; 4 quantising launches
-    instead of 7 (+ the norm and activation kernels they replace).  Secondary figure: the headline step keeps one
-    act-quant launch per linear."""
+def fused_block_leg(F, torch, dev, fused, acts):
+    """The same GEMMs wired the way a Llama block uses them, with the producer fusions (§8f-2): RMSNorm -> int8 feeds
+    the fused q/k/v GEMM and the fused gate/up GEMM, silu(gate)*up -> int8 is written straight from the gate/up
+    output: 4 quantising launches that also do the norm / activation work + 4 GEMMs = 8 launches."""
     M = M_TOKENS
     w_norm = torch.ones(4096, dtype=torch.bfloat16, device=dev)
     qa = (F.alloc_q(M, 4096, dev), torch.empty(M, dtype=torch.float32, device=dev))
     qo = (F.alloc_q(M, 4096, dev), torch.empty(M, dtype=torch.float32, device=dev))
     qm = (F.alloc_q(M, 4096, dev), torch.empty(M, dtype=torch.float32, device=dev))
     qh = (F.alloc_q(M, 11008, dev), torch.empty(M, dtype=torch.float32, device=dev))
-    outs = {n: torch.empty(M, nn_, dtype=torch.bfloat16, device=dev) for n, k, nn_, _ in LINEARS}
+    outs = {g: torch.empty(M, fused[g].out_features, dtype=torch.bfloat16, device=dev) for g in fused}
 
     def gemm(name, q):
-        m = mods[name]
+        m = fused[name]
         F.qgemm(q[0], q[1], m.qweight, m.weight_scale, m.bias, torch.bfloat16, out=outs[name])
 
     def block():
         F.rmsnorm_quant(acts["x_attn"], w_norm, out=qa)
-        for n in ("q_proj", "k_proj", "v_proj"):
-            gemm(n, qa)
+        gemm("qkv_proj", qa)
         F.quantize_act(acts["attn_out"], out=qo)          # attention itself is outside the path
         gemm("o_proj", qo)
         F.rmsnorm_quant(outs["o_proj"], w_norm, out=qm)   # post-attention norm reads the o_proj output
-        gemm("gate_proj", qm)
-        gemm("up_proj", qm)
-        F.act_mul_quant(outs["gate_proj"], outs["up_proj"], act="silu", out=qh)
-        gemm("down_proj", qh)
-
-    block()
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        block()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        block()
-    for _ in range(3):
-        g.replay()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(50):
-        g.replay()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 50
-    res = {"ms_per_block": ms, "tops": OPS_PER_STEP / (ms * 1e-3) / 1e12, "tokens_per_s": M / (ms * 1e-3),
-           "launches": 11, "note": "7 GEMMs + rmsnorm_quant x2 + act_quant + silu_mul_quant, CUDA-graph replay x50"}
-    # the same block with q/k/v and gate/up fused into one GEMM each (fuse_linears: exact, per-channel scales):
-    # 4 GEMMs + 4 quantising kernels = 8 launches
-    import protoquant_b200 as pq
-    qkv = pq.fuse_linears([mods["q_proj"], mods["k_proj"], mods["v_proj"]])
-    gate_up = pq.fuse_linears([mods["gate_proj"], mods["up_proj"]])
-    y_qkv = torch.empty(M, 3 * 4096, dtype=torch.bfloat16, device=dev)
-    y_gu = torch.empty(M, 2 * 11008, dtype=torch.bfloat16, device=dev)
-
-    def block8():
-        F.rmsnorm_quant(acts["x_attn"], w_norm, out=qa)
-        F.qgemm(qa[0], qa[1], qkv.qweight, qkv.weight_scale, qkv.bias, torch.bfloat16, out=y_qkv)
-        F.quantize_act(acts["attn_out"], out=qo)
-        gemm("o_proj", qo)
-        F.rmsnorm_quant(outs["o_proj"], w_norm, out=qm)
-        F.qgemm(qm[0], qm[1], gate_up.qweight, gate_up.weight_scale, gate_up.bias, torch.bfloat16, out=y_gu)
+        gemm("gate_up_proj", qm)
+        y_gu = outs["gate_up_proj"]
         F.act_mul_quant(y_gu[:, :11008], y_gu[:, 11008:], act="silu", out=qh)
         gemm("down_proj", qh)
 
-    block8()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        block8()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g8 = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g8):
-        block8()
-    for _ in range(3):
-        g8.replay()
-    a.record()
-    for _ in range(50):
-        g8.replay()
-    b.record()
-    torch.cuda.synchronize()
-    ms8 = a.elapsed_time(b) / 50
-    res["fused_qkv_gate_up"] = {"ms_per_block": ms8, "tops": OPS_PER_STEP / (ms8 * 1e-3) / 1e12,
-                                "tokens_per_s": M / (ms8 * 1e-3), "launches": 8}
-    del qkv, gate_up
-    return res
+    run, _ = capture(torch, dev, block)
+    ms = timed(torch, run, 50) / 50
+    return {"ms_per_block": ms, "tops": OPS_PER_STEP / (ms * 1e-3) / 1e12, "tokens_per_s": M / (ms * 1e-3), "launches": 8,
+            "note": "rmsnorm_quant x2 + act_quant + silu_mul_quant + 4 GEMMs (qkv and gate/up fused), CUDA-graph replay x50"}
 
 
 def sharded_leg(pq, torch, dist, dev, rank, world):

@@ -11,7 +11,16 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - the caller owns all buffers; nothing is allocated or freed here, except
- *     the opaque pq_linear handle of the host-buffer convenience API;
+ *     the opaque pq_linear handle of the host-buffer convenience API and a
+ *     per-stream int32 workspace of the stream-K schedule (first use, never
+ *     during stream capture);
+ *   - process-wide state is limited to caches that cannot change results: the
+ *     per-device capability / kernel-attribute flags, encoded TMA descriptors
+ *     (pure functions of address, shape and stride) and that workspace pool.
+ *     Entry points may be called concurrently from several threads on distinct
+ *     streams.  The exported pq_debug_* symbols are test / profiling hooks, not
+ *     part of this API: relaxed atomics that select between code paths with
+ *     bit-identical results;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no
  *     function synchronises unless it says so;
  *   - return value 0 = ok, non-zero = PQ_ERR_*; pq_last_error() returns a
@@ -99,6 +108,19 @@ int pq_qgemm_multi(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
                    void* const* ys, int n_ys, int y_dtype, int64_t ldy,
                    int64_t M, int64_t N, int64_t K, void* stream);
 
+/* SURVEY §8e, one call per forward of a column-parallel shard: act-quant into the caller's workspace (as pq_qlinear)
+ * followed by the fused GEMM + all-gather store (as pq_qgemm_multi).  flags: PQ_MULTI_MULTICAST = ys[0] is an NVSwitch
+ * multicast address (n_ys must be 1): the epilogue then writes it with multimem.st and the switch replicates the
+ * tile into every rank; without the flag every ys[d] is a unicast (local or NVLink peer-mapped) address and is
+ * written with TMA bulk stores.  Two kernel launches, no sync; the caller issues the cross-rank barrier. */
+enum pq_multi_flags { PQ_MULTI_MULTICAST = 1 };
+int pq_qlinear_multi(const void* x, int x_dtype, int64_t ldx,
+                     const int8_t* Wq, int64_t ldb, const float* s_w, const float* bias,
+                     void* const* ys, int n_ys, int y_dtype, int64_t ldy,
+                     int8_t* xq_ws, float* sx_ws,
+                     int64_t M, int64_t N, int64_t K,
+                     const pq_quant_spec* spec, int flags, void* stream);
+
 /* Parity hook for row a3: raw int32 accumulators acc[M,N], row stride ldc (elements). */
 int pq_qgemm_i32(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
                  int32_t* acc, int64_t ldc,
@@ -166,7 +188,9 @@ int pq_reduce_dequant(const int32_t* const* parts, int n_parts, int64_t ld_part,
                       void* const* ys, int n_ys, int y_dtype, int64_t ldy,
                       int64_t M, int64_t N, void* stream);
 
-/* Host-buffer convenience API (what bench.py's "e2e" number goes through).
+/* Host-buffer convenience API: the whole path behind one call on HOST buffers (H2D copy, act-quant, GEMM, D2H
+ * copy).  bench.py's "e2e" figure goes through the Python module API (DynamicQuantLinear.forward with pinned host
+ * tensors and torch copies inside the timed region); this handle is the same thing for a C caller.
  * A pq_linear owns device copies of (Wq, s_w, bias), a device activation/output
  * workspace for up to max_tokens rows, and a private stream. */
 typedef struct pq_linear pq_linear;

@@ -6,15 +6,16 @@ No Triton, no backend dispatch, no CPU fallback.
 from ._lib import ProtoquantError, launch_count, lib
 from .functional import (DEFAULT_SPEC, QuantSpec, act_mul_quant, dequantize as dequantize_tensor, layernorm_quant,
                          norm_quant, qgemm, qgemm_i32, qlinear, quantize_act, quantize_weight, rmsnorm_quant)
-from .modules import DynamicQuantLinear, fuse_linears, swap_linear
+from .modules import DynamicQuantLinear, SharedInputLinear, fuse_linears, swap_linear
 from .qtensor import QTensor, dequantize, quantize
-from .sharded import ParallelGatedMLP, RowParallelDynamicQuantLinear, ShardedDynamicQuantLinear, maybe_shard, shard_bounds
+from .sharded import (ParallelGatedMLP, RowParallelDynamicQuantLinear, ShardedDynamicQuantLinear, TokenAdaptiveLinear,
+                      maybe_shard, shard_bounds)
 
 __version__ = "0.1.0"
 __all__ = [
     "ProtoquantError", "launch_count", "lib", "QuantSpec", "DEFAULT_SPEC",
     "quantize_act", "quantize_weight", "qgemm", "qgemm_i32", "qlinear", "dequantize_tensor",
     "norm_quant", "rmsnorm_quant", "layernorm_quant", "act_mul_quant",
-    "QTensor", "quantize", "dequantize", "DynamicQuantLinear", "swap_linear", "fuse_linears",
-    "ShardedDynamicQuantLinear", "RowParallelDynamicQuantLinear", "ParallelGatedMLP", "maybe_shard", "shard_bounds",
+    "QTensor", "quantize", "dequantize", "DynamicQuantLinear", "SharedInputLinear", "swap_linear", "fuse_linears",
+    "ShardedDynamicQuantLinear", "RowParallelDynamicQuantLinear", "ParallelGatedMLP", "TokenAdaptiveLinear", "maybe_shard", "shard_bounds",
 ]

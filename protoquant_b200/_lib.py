@@ -17,11 +17,12 @@ LIB_PATH = os.environ.get("PQ_LIB_PATH") or os.path.join(_HERE, "libprotoquant_b
 PQ_F32, PQ_F16, PQ_BF16, PQ_I32 = 0, 1, 2, 3
 PQ_DIV, PQ_RCP_MUL, PQ_INV_SCALE = 0, 1, 2
 PQ_ACT_IDENTITY, PQ_ACT_SILU, PQ_ACT_GELU, PQ_ACT_GELU_TANH = 0, 1, 2, 3
+PQ_MULTI_MULTICAST = 1
 
 # every symbol include/protoquant_b200.h declares (tests/test_abi.py checks the .so exports them)
 EXPORTS = (
     "pq_version", "pq_last_error", "pq_launch_count", "pq_act_quant", "pq_weight_quant",
-    "pq_qgemm", "pq_qgemm_multi", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
+    "pq_qgemm", "pq_qgemm_multi", "pq_qlinear_multi", "pq_qgemm_i32", "pq_dequant", "pq_qlinear",
     "pq_linear_create", "pq_linear_forward_host", "pq_linear_destroy",
     "pq_norm_quant", "pq_act_mul_quant",
     "pq_row_absmax", "pq_act_quant_amax", "pq_qgemm_i32_scatter", "pq_reduce_dequant",
@@ -58,6 +59,8 @@ def _declare(lib):
     lib.pq_qgemm.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp]
     lib.pq_qgemm_multi.restype = i32
     lib.pq_qgemm_multi.argtypes = [vp, i64, vp, i64, vp, vp, vp, c.POINTER(vp), i32, i32, i64, i64, i64, i64, vp]
+    lib.pq_qlinear_multi.restype = i32
+    lib.pq_qlinear_multi.argtypes = [vp, i32, i64, vp, i64, vp, vp, c.POINTER(vp), i32, i32, i64, vp, vp, i64, i64, i64, specp, i32, vp]
     lib.pq_qgemm_i32.restype = i32
     lib.pq_qgemm_i32.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
     lib.pq_dequant.restype = i32
@@ -88,7 +91,7 @@ def _declare(lib):
     if hasattr(lib, "pq_debug_set_timeline"):
         lib.pq_debug_set_timeline.restype = None
         lib.pq_debug_set_timeline.argtypes = [vp]
-    for dbg in ("pq_debug_set_gemm_config", "pq_debug_set_streamk", "pq_debug_set_pdl", "pq_debug_set_staged", "pq_debug_set_prefetch", "pq_debug_set_fused_decode", "pq_debug_set_tma_store", "pq_debug_set_epilogue", "pq_debug_set_narrow_tiles", "pq_debug_set_weight_prefetch"):
+    for dbg in ("pq_debug_set_gemm_config", "pq_debug_set_streamk", "pq_debug_set_pdl", "pq_debug_set_staged", "pq_debug_set_prefetch", "pq_debug_set_fused_decode", "pq_debug_set_tma_store", "pq_debug_set_epilogue", "pq_debug_set_narrow_tiles", "pq_debug_set_weight_prefetch", "pq_debug_set_multi_tma"):
         if hasattr(lib, dbg):
             getattr(lib, dbg).restype = None
             getattr(lib, dbg).argtypes = [i32]

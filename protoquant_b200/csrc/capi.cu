@@ -96,6 +96,27 @@ int pq_qgemm_multi(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
   return launch_qgemm(xq, lda, Wq, ldb, s_x, s_w, bias, ys, n_ys, y_dtype, ldy, M, N, K, (cudaStream_t)stream);
 }
 
+int pq_qlinear_multi(const void* x, int x_dtype, int64_t ldx,
+                     const int8_t* Wq, int64_t ldb, const float* s_w, const float* bias,
+                     void* const* ys, int n_ys, int y_dtype, int64_t ldy,
+                     int8_t* xq_ws, float* sx_ws,
+                     int64_t M, int64_t N, int64_t K,
+                     const pq_quant_spec* spec, int flags, void* stream) {
+  if (M == 0) return PQ_OK;
+  if (!xq_ws || !sx_ws) PQ_FAIL(PQ_ERR_ARG, "pq_qlinear_multi: null workspace");
+  if (y_dtype != PQ_BF16 && y_dtype != PQ_F16 && y_dtype != PQ_F32)
+    PQ_FAIL(PQ_ERR_ARG, "pq_qlinear_multi: y_dtype must be PQ_BF16, PQ_F16 or PQ_F32");
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  const int64_t ldq = (K + 15) / 16 * 16;
+  const long long w_bytes = (M > 64 && Wq && N > 0 && ldb >= K) ? (long long)(N - 1) * ldb + K : 0;
+  rc = launch_rowwise_quant(x, x_dtype, M, K, ldx, xq_ws, ldq, sx_ws, 0, resolve_spec(spec), (cudaStream_t)stream,
+                            Wq, w_bytes < (64LL << 20) ? w_bytes : (64LL << 20));
+  if (rc) return rc;
+  return launch_qgemm(xq_ws, ldq, Wq, ldb, sx_ws, s_w, bias, ys, n_ys, y_dtype, ldy, M, N, K, (cudaStream_t)stream, 0,
+                      (flags & PQ_MULTI_MULTICAST) ? 1 : 0);
+}
+
 int pq_qgemm_i32(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
                  int32_t* acc, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream) {
   void* outs[1] = {acc};

@@ -33,7 +33,8 @@ struct SmallArgs {
   const float* s_x;
   const float* s_w;
   const float* bias;
-  void* out;
+  void* out[8];     // the [M,N] result goes to each of out[0..n_out): local buffer and NVLink peers (fused all-gather)
+  int n_out;
   long long ldo;
 };
 
@@ -237,8 +238,9 @@ qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
         v = __fmul_rn(v, __ldg(g.s_w + n));
         if (g.bias != nullptr) v = __fadd_rn(v, __ldg(g.bias + n));   // no add at all without bias (-0.0 stays -0.0)
       }
-      store_one<OutT>(g.out, (long long)m * g.ldo + n, v, acc);
+      for (int d = 0; d < g.n_out; ++d) store_one<OutT>(g.out[d], (long long)m * g.ldo + n, v, acc);
     }
+    if (g.n_out > 1) __threadfence_system();   // peer stores ordered before the kernel (and the caller's barrier) ends
   }
 
   if (S > 1) cluster_sync(); else __syncthreads();   // peers may still be reading our partial
@@ -659,14 +661,17 @@ int launch_small_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ld
 
 int launch_qgemm_smallm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                         const float* s_x, const float* s_w, const float* bias,
-                        void* out, int out_dtype, int64_t ldo,
+                        void* const* outs, int n_out, int out_dtype, int64_t ldo,
                         int64_t M, int64_t N, int64_t K, int num_sms, cudaStream_t stream) {
   if (M < 1 || M > 64) PQ_FAIL(PQ_ERR_ARG, "small-M GEMM needs 1 <= M <= 64");
+  if (n_out < 1 || n_out > 8) PQ_FAIL(PQ_ERR_ARG, "small-M GEMM: 1..8 destinations");
   SmallArgs g = {};
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.num_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
   g.s_x = s_x; g.s_w = s_w; g.bias = bias;
-  g.out = out; g.ldo = ldo;
+  for (int d = 0; d < n_out; ++d) g.out[d] = outs[d];
+  g.n_out = n_out;
+  g.ldo = ldo;
   switch (out_dtype) {
     case PQ_BF16: return launch_small_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
     case PQ_F16: return launch_small_typed<__half>(a, lda, b, ldb, g, num_sms, stream);

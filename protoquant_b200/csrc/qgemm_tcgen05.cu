@@ -27,7 +27,7 @@
 namespace pq {
 int launch_qgemm_smallm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                         const float* s_x, const float* s_w, const float* bias,
-                        void* out, int out_dtype, int64_t ldo,
+                        void* const* outs, int n_out, int out_dtype, int64_t ldo,
                         int64_t M, int64_t N, int64_t K, int num_sms, cudaStream_t stream);
 namespace {
 
@@ -69,13 +69,11 @@ struct GemmArgs {
 // OUT_BYTES: 2 = bf16 / fp16, 4 = fp32, 0 = int32 accumulators.
 constexpr int NUM_BARS_C(int stages) { return 2 * stages + 4; }
 
-// Output tensor maps.  The staged epilogue (fused all-gather / reduce-scatter) can hand its shared-memory tile to
-// TMA bulk stores towards up to 8 destinations (the local buffer and the peers' buffers over NVLink), so it takes
-// one tensor map per destination; every other instantiation needs a single map.
+// Output tensor maps: one per destination.  Both TMA-store epilogues (per-warp boxes and the CTA-staged tile) can
+// write a finished tile to up to 8 destinations -- the local buffer and the peers' buffers over NVLink (fused
+// all-gather), or one inbox per column block (reduce-scatter, staged epilogue only).
 struct OutMaps { CUtensorMap m[8]; };
-template <bool STAGED> struct YMap { using type = CUtensorMap; };
-template <> struct YMap<true> { using type = OutMaps; };
-__device__ __forceinline__ const CUtensorMap* ymap(const CUtensorMap& t, int) { return &t; }
+template <bool STAGED> struct YMap { using type = OutMaps; };
 __device__ __forceinline__ const CUtensorMap* ymap(const OutMaps& t, int d) { return &t.m[d]; }
 template <int CG, int BN, int STAGES, bool STAGED = false, int OUT_BYTES = 4>
 struct SmemLayout {
@@ -247,8 +245,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (g.tma_store) {
-      const int nmaps = STAGED ? g.n_out : 1;
-      for (int d = 0; d < nmaps; ++d) prefetch_tmap(ymap(tmap_y, d));
+      for (int d = 0; d < g.n_out; ++d) prefetch_tmap(ymap(tmap_y, d));
     }
   }
   if (warp == 1 && lane == 0) {
@@ -711,8 +708,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (row0 < g.M && col0 + ct < g.N && !(g.dbg & 1))
-                tma_store_2d(ymap(tmap_y, 0), ws_u32 + buf * L::WS_BOX, col0 + ct, row0);
+              if (row0 < g.M && col0 + ct < g.N && !(g.dbg & 1)) {
+                for (int d = 0; d < g.n_out; ++d)      // n_out > 1: the local buffer and every NVLink peer (fused all-gather)
+                  tma_store_2d(ymap(tmap_y, d), ws_u32 + buf * L::WS_BOX, col0 + ct, row0);
+              }
               tma_store_commit();
             }
           }
@@ -809,7 +808,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (g.n_out > 1 || g.scatter_cols > 0) __threadfence_system();
       }
     } else if constexpr (L::WS_NBUF > 0) {
-      if (g.tma_store && lane == 0) tma_store_wait<0>();
+      if (g.tma_store && lane == 0) {
+        tma_store_wait<0>();
+        if (g.n_out > 1) __threadfence_system();   // peer writes are complete and ordered before the kernel ends
+      }
     }
   }
 
@@ -838,7 +840,9 @@ struct SkPool {
 SkPool g_sk_pool[64];
 std::atomic<unsigned long long*> g_timeline{nullptr};
 Knob g_tma_store{1};     // staged epilogue uses TMA bulk stores when it can (pq_debug_set_tma_store)
-Knob g_multi_tma{1};     // multi-destination (NVLink) epilogues hand their tiles to TMA stores (pq_debug_set_multi_tma)
+Knob g_multi_tma{0};     // multi-destination (NVLink) epilogues: 0 = CTA-staged tile + LSU 256-byte stores (default: measured
+                         // fastest over NVLink, profiles/README_r2.md); 1 = CTA-staged tile + TMA stores; 2 = per-warp TMA
+                         // boxes with the regular tile heuristic (pq_debug_set_multi_tma)
 Knob g_sk_mode{-1};  // -1 heuristic (default: single-wave long-K problems only), 0 never, 1 whenever legal
 
 bool sk_alloc_slot(SkPool& pool, int num_sms) {
@@ -925,14 +929,24 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
       }
       if (ok) g.tma_store = 1;
     }
-  } else if (L::WS_NBUF > 0 && g.n_out == 1 && tma_ok) {
+  } else if (L::WS_NBUF > 0 && tma_ok) {
     // per-warp epilogue boxes: [32 rows] x [32 columns]; 64B swizzle for 16-bit outputs, 128B swizzle for fp32
     constexpr int esz = (int)sizeof(OutT);
-    if (encode_tmap_2d(&ty, g.out[0], esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
-                       (uint64_t)g.N, (uint64_t)g.M, (uint64_t)(g.ldo * esz), 32, 32,
-                       esz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                       CU_TENSOR_MAP_L2_PROMOTION_NONE) == PQ_OK)
-      g.tma_store = 1;
+    bool ok = true;
+    for (int d = 0; d < g.n_out && ok; ++d)
+      ok = encode_tmap_2d(&ty.m[d], g.out[d], esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                          (uint64_t)g.N, (uint64_t)g.M, (uint64_t)(g.ldo * esz), 32, 32,
+                          esz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE) == PQ_OK;
+    if (ok) g.tma_store = 1;
+  }
+  // several destinations without a TMA path would fall back to one-row-per-lane 16-byte peer stores (measured 4x
+  // slower over NVLink than coalesced segments): the caller routes those launches to the staged epilogue instead
+  if constexpr (!STAGED) {
+    if (g.n_out > 1 && !g.tma_store) {
+      if (g.M > 128) return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g0, num_sms, st);
+      return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g0, num_sms, st);
+    }
   }
   auto kern = qgemm_kernel<CG, BN, STAGES, OutT, STAGED, MC>;
   static PerDeviceOnce once;   // function attributes are per device: set them on every device this process drives
@@ -1024,7 +1038,15 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
   //   cfg 0: 1-CTA 128x256   cfg 1: 2-CTA 256x256   cfg 2: 1-CTA 128x128   cfg 3: 1-CTA 128x64
   //   cfg 16: 4-CTA multicast cluster, 512x256 super-tiles (experiment: no faster, see README_r1.md)
   //   cfg 4: 2-CTA 256x128   cfg 8/9/10: 2-CTA 256x{240,224,208}   cfg 11/12/13: 1-CTA 128x{240,224,208}
-  if (g.n_out > 1 || g.scatter_cols > 0 || (g_force_staged && !std::is_same<OutT, int32_t>::value)) {
+  // Fused all-gather (n_out > 1) / reduce-scatter: the CTA-staged epilogue (256-column tiles) writes whole 256-byte row
+  // segments to every destination with LSU stores.  Measured on 8 x B200 (2048 x 3584 x 8192 shard, 103 MB to 7 peers):
+  // LSU 256-byte segments 208 us, multimem.st 210 us, CTA-staged TMA stores (128-byte rows) 305 us, per-warp TMA boxes
+  // (64-byte rows, any tile shape: g_multi_tma == 2) 336 us -- TMA writes reach NVLink as small requests, so the TMA
+  // variants stay behind the knob.
+  const bool per_warp_multi = g.n_out > 1 && g.scatter_cols == 0 && !g.multimem && sizeof(OutT) == 2 && g.vec_ok &&
+                              g_multi_tma == 2 && g_tma_store != 0 && g.M > 128 && g_force_cfg < 0;
+  if ((g.n_out > 1 && !per_warp_multi) || g.scatter_cols > 0 || g.multimem ||
+      (g_force_staged && !std::is_same<OutT, int32_t>::value)) {
     // fused all-gather / reduce-scatter: coalesced (shared-memory staged) stores to the peer destinations
     if (g.M > 128) return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
     return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
@@ -1116,7 +1138,7 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,
                  void* const* outs, int n_out, int out_dtype, int64_t ldo,
-                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols) {
+                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols, int multimem) {
   if (M < 0 || N < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "qgemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   if (M == 0 || N == 0) return PQ_OK;
   if (M > 0x7fffff00LL || N > 0x7fffff00LL || K > 0x7fffff00LL) PQ_FAIL(PQ_ERR_ARG, "qgemm: dimension too large");
@@ -1138,8 +1160,10 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   // ... unless K is short: the cluster split-K machinery then costs more than it saves (64 x 4096 x 1024:
   // 11.4 us vs 5.0 us with 128x64 tiles; 64 x 4096 x 2048: 9.2 vs 6.4 us; 48 x 4096 x 4096: 8.3 vs 9.4 us).
   const bool smallm_pays = !(M > 32 && K <= 2048);
-  if (M <= 64 && n_out == 1 && scatter_cols == 0 && !g_force_staged && g_sk_mode != 1 && ((g_force_cfg < 0 && smallm_pays) || g_force_cfg == 7))
-    return launch_qgemm_smallm(a, lda, b, ldb, s_x, s_w, bias, outs[0], out_dtype, ldo, M, N, K, num_sms, stream);
+  // (several destinations = fused all-gather of a decode batch: the weight-streaming kernel writes its few rows to every
+  // peer itself -- 16 x 3584 shard on 8 GPUs: 9.6 us, against 31 us for 128-row tiles with the staged epilogue)
+  if (M <= 64 && scatter_cols == 0 && !multimem && !g_force_staged && g_sk_mode != 1 && ((g_force_cfg < 0 && smallm_pays) || g_force_cfg == 7))
+    return launch_qgemm_smallm(a, lda, b, ldb, s_x, s_w, bias, outs, n_out, out_dtype, ldo, M, N, K, num_sms, stream);
   if (g_force_cfg == 7) PQ_FAIL(PQ_ERR_ARG, "qgemm: config 7 (small-M kernel) needs M <= 64");
   GemmArgs g = {};
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
@@ -1156,6 +1180,11 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   g.prefetch_b = g_prefetch_b;
   g.dbg = g_epi_dbg;
   g.scatter_cols = (int)scatter_cols;
+  if (multimem) {
+    if (n_out != 1 || scatter_cols != 0 || !g.vec_ok || (N * esz) % 16 != 0)
+      PQ_FAIL(PQ_ERR_ARG, "qgemm: a multicast destination needs n_ys == 1 and 16-byte aligned rows / row length");
+    g.multimem = 1;
+  }
   switch (out_dtype) {
     case PQ_BF16: return launch_typed<__nv_bfloat16>(a, lda, b, ldb, g, num_sms, stream);
     case PQ_F16: return launch_typed<__half>(a, lda, b, ldb, g, num_sms, stream);

@@ -31,13 +31,39 @@ class QuantSpec:
 DEFAULT_SPEC = QuantSpec()
 
 
-def _stream() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None) -> ctypes.c_void_p:
+    """The current stream of `device` (default: the current device) as the void* the C ABI takes."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise _lib.ProtoquantError(f"{name} must be a CUDA tensor: protoquant_b200 has no CPU fallback")
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(t: torch.Tensor, *others):
+    """Device guard for one C-ABI call: the library launches on the CURRENT device, so make the device that owns
+    `t` current for the duration of the call (a no-op when it already is), and insist that every other tensor
+    argument lives on the same device -- single-process model parallelism (HF device_map, pipeline stages) calls
+    modules whose weights are on cuda:1 while cuda:0 is current."""
+    dev = t.device
+    for o in others:
+        if o is not None and o.device != dev:
+            raise _lib.ProtoquantError(f"all tensor arguments must be on one device: got {dev} and {o.device}")
+    if dev.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(dev)
 
 
 def _pad16(k: int) -> int:
@@ -77,8 +103,9 @@ def quantize_act(x: torch.Tensor, transpose: bool = False, spec: Optional[QuantS
         xq, s = out
     if M == 0:
         return xq, s
-    rc = _lib.lib().pq_act_quant(x.data_ptr(), _DT[x.dtype], M, K, x.stride(0), xq.data_ptr(), xq.stride(0),
-                                 s.data_ptr(), int(transpose), _specp(spec), _stream())
+    with _on(x, xq, s):
+        rc = _lib.lib().pq_act_quant(x.data_ptr(), _DT[x.dtype], M, K, x.stride(0), xq.data_ptr(), xq.stride(0),
+                                     s.data_ptr(), int(transpose), _specp(spec), _stream(x.device))
     _lib.check(rc, "pq_act_quant")
     return xq, s
 
@@ -93,8 +120,9 @@ def quantize_weight(w: torch.Tensor, spec: Optional[QuantSpec] = None) -> Tuple[
     wq = alloc_q(N, K, w.device)
     s = torch.empty((N,), dtype=torch.float32, device=w.device)
     if N:
-        rc = _lib.lib().pq_weight_quant(w.data_ptr(), _DT[w.dtype], N, K, w.stride(0), wq.data_ptr(), wq.stride(0),
-                                        s.data_ptr(), _specp(spec), _stream())
+        with _on(w):
+            rc = _lib.lib().pq_weight_quant(w.data_ptr(), _DT[w.dtype], N, K, w.stride(0), wq.data_ptr(), wq.stride(0),
+                                            s.data_ptr(), _specp(spec), _stream(w.device))
         _lib.check(rc, "pq_weight_quant")
     return wq, s
 
@@ -120,8 +148,9 @@ def qgemm_i32(xq: torch.Tensor, wq: torch.Tensor) -> torch.Tensor:
         raise ValueError("K mismatch")
     acc = torch.empty((M, N), dtype=torch.int32, device=xq.device)
     if M and N:
-        rc = _lib.lib().pq_qgemm_i32(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), acc.data_ptr(), N,
-                                     M, N, K, _stream())
+        with _on(xq, wq):
+            rc = _lib.lib().pq_qgemm_i32(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), acc.data_ptr(), N,
+                                         M, N, K, _stream(xq.device))
         _lib.check(rc, "pq_qgemm_i32")
     return acc
 
@@ -150,9 +179,10 @@ def qgemm(xq: torch.Tensor, s_x: torch.Tensor, wq: torch.Tensor, s_w: torch.Tens
             raise ValueError("bias size mismatch")
     y = out if out is not None else torch.empty((M, N), dtype=out_dtype, device=xq.device)
     if M and N:
-        rc = _lib.lib().pq_qgemm(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), s_x.data_ptr(),
-                                 s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                 y.data_ptr(), _DT[y.dtype], y.stride(0), M, N, K, _stream())
+        with _on(xq, wq, s_x, s_w, bias, y):
+            rc = _lib.lib().pq_qgemm(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), s_x.data_ptr(),
+                                     s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                     y.data_ptr(), _DT[y.dtype], y.stride(0), M, N, K, _stream(xq.device))
         _lib.check(rc, "pq_qgemm")
     return y
 
@@ -173,9 +203,10 @@ def qgemm_multi(xq: torch.Tensor, s_x: torch.Tensor, wq: torch.Tensor, s_w: torc
         bias = bias.to(torch.float32).contiguous()
     arr = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
     if M and N:
-        rc = _lib.lib().pq_qgemm_multi(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), s_x.data_ptr(),
-                                       s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                       arr, len(dest_ptrs), _DT[out_dtype], ldy, M, N, K, _stream())
+        with _on(xq, wq, s_x, s_w, bias):
+            rc = _lib.lib().pq_qgemm_multi(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), s_x.data_ptr(),
+                                           s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                           arr, len(dest_ptrs), _DT[out_dtype], ldy, M, N, K, _stream(xq.device))
         _lib.check(rc, "pq_qgemm_multi")
 
 
@@ -198,12 +229,44 @@ def qlinear_into(x2: torch.Tensor, wq_storage: torch.Tensor, in_features: int, s
     xq_ws [M, ld16(K)] int8 and sx_ws [M] fp32 scratch.  No allocation, no checks beyond the C ABI's."""
     M, N, K = x2.shape[0], wq_storage.shape[0], in_features
     if M:
-        rc = _lib.lib().pq_qlinear(x2.data_ptr(), _DT[x2.dtype], x2.stride(0), wq_storage.data_ptr(), wq_storage.stride(0),
-                                   s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                   y.data_ptr(), _DT[y.dtype], y.stride(0), xq_ws.data_ptr(), sx_ws.data_ptr(), M, N, K,
-                                   _specp(spec), _stream())
+        with _on(x2, wq_storage, s_w, bias, y, xq_ws, sx_ws):
+            rc = _lib.lib().pq_qlinear(x2.data_ptr(), _DT[x2.dtype], x2.stride(0), wq_storage.data_ptr(), wq_storage.stride(0),
+                                       s_w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       y.data_ptr(), _DT[y.dtype], y.stride(0), xq_ws.data_ptr(), sx_ws.data_ptr(), M, N, K,
+                                       _specp(spec), _stream(x2.device))
         _lib.check(rc, "pq_qlinear")
     return y
+
+
+def qlinear_multi_into(x2: torch.Tensor, wq_storage: torch.Tensor, in_features: int, s_w: torch.Tensor,
+                       bias: Optional[torch.Tensor], dest_ptrs, ldy: int, out_dtype: torch.dtype,
+                       xq_ws: torch.Tensor, sx_ws: torch.Tensor, spec: Optional[QuantSpec] = None,
+                       multicast: bool = False) -> None:
+    """One `pq_qlinear_multi` call: act-quant into the caller's workspace + GEMM whose epilogue stores the [M, N]
+    result into every raw device address of `dest_ptrs` (row stride `ldy` elements): the local output buffer and
+    the peers' buffers over NVLink (TMA bulk stores), or, with `multicast`, one NVSwitch multicast address
+    (multimem.st).  The caller issues the cross-rank barrier afterwards."""
+    _require_cuda(x2, "x")
+    M, N, K = x2.shape[0], wq_storage.shape[0], in_features
+    if x2.dim() != 2 or x2.stride(1) != 1 or x2.dtype not in _DT:
+        raise TypeError("x must be a 2-D tensor of a supported dtype with unit column stride")
+    if not (1 <= len(dest_ptrs) <= 8) or (multicast and len(dest_ptrs) != 1):
+        raise ValueError("1..8 destinations (exactly 1 with multicast)")
+    for t, n in ((s_w, "s_w"), (bias, "bias")):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise TypeError(f"{n} must be a contiguous fp32 tensor")
+    if xq_ws.shape[0] < M or xq_ws.shape[1] < _pad16(K) or xq_ws.stride(0) % 16 or sx_ws.numel() < M:
+        raise ValueError("act-quant workspace too small")
+    arr = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
+    if M and N:
+        with _on(x2, wq_storage, s_w, bias, xq_ws, sx_ws):
+            rc = _lib.lib().pq_qlinear_multi(x2.data_ptr(), _DT[x2.dtype], x2.stride(0), wq_storage.data_ptr(),
+                                             wq_storage.stride(0), s_w.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, arr, len(dest_ptrs),
+                                             _DT[out_dtype], ldy, xq_ws.data_ptr(), sx_ws.data_ptr(), M, N, K,
+                                             _specp(spec), _lib.PQ_MULTI_MULTICAST if multicast else 0,
+                                             _stream(x2.device))
+        _lib.check(rc, "pq_qlinear_multi")
 
 
 def row_absmax(x: torch.Tensor) -> torch.Tensor:
@@ -213,8 +276,9 @@ def row_absmax(x: torch.Tensor) -> torch.Tensor:
     M, K = x2.shape
     amax = torch.empty((M,), dtype=torch.float32, device=x.device)
     if M:
-        _lib.check(_lib.lib().pq_row_absmax(x2.data_ptr(), _DT[x2.dtype], M, K, x2.stride(0), amax.data_ptr(), _stream()),
-                   "pq_row_absmax")
+        with _on(x2):
+            rc = _lib.lib().pq_row_absmax(x2.data_ptr(), _DT[x2.dtype], M, K, x2.stride(0), amax.data_ptr(), _stream(x2.device))
+        _lib.check(rc, "pq_row_absmax")
     return amax
 
 
@@ -229,9 +293,10 @@ def quantize_act_with_amax(x: torch.Tensor, amax: torch.Tensor, spec: Optional[Q
     xq = alloc_q(M, K, x.device)
     s_x = torch.empty((M,), dtype=torch.float32, device=x.device)
     if M:
-        _lib.check(_lib.lib().pq_act_quant_amax(x.data_ptr(), _DT[x.dtype], M, K, x.stride(0), amax.data_ptr(),
-                                                xq.data_ptr(), xq.stride(0), s_x.data_ptr(), _specp(spec), _stream()),
-                   "pq_act_quant_amax")
+        with _on(x, amax):
+            rc = _lib.lib().pq_act_quant_amax(x.data_ptr(), _DT[x.dtype], M, K, x.stride(0), amax.data_ptr(),
+                                              xq.data_ptr(), xq.stride(0), s_x.data_ptr(), _specp(spec), _stream(x.device))
+        _lib.check(rc, "pq_act_quant_amax")
     return xq, s_x
 
 
@@ -245,9 +310,10 @@ def qgemm_i32_scatter(xq: torch.Tensor, wq: torch.Tensor, dest_ptrs, ld_dest: in
     N = wq.shape[0]
     arr = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
     if M and N:
-        _lib.check(_lib.lib().pq_qgemm_i32_scatter(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), arr,
-                                                   len(dest_ptrs), ld_dest, cols_per_dest, M, N, K, _stream()),
-                   "pq_qgemm_i32_scatter")
+        with _on(xq, wq):
+            rc = _lib.lib().pq_qgemm_i32_scatter(xq.data_ptr(), xq.stride(0), wq.data_ptr(), wq.stride(0), arr,
+                                                 len(dest_ptrs), ld_dest, cols_per_dest, M, N, K, _stream(xq.device))
+        _lib.check(rc, "pq_qgemm_i32_scatter")
 
 
 def reduce_dequant(part_ptrs, ld_part: int, s_x: torch.Tensor, s_w: torch.Tensor, bias: Optional[torch.Tensor],
@@ -256,9 +322,11 @@ def reduce_dequant(part_ptrs, ld_part: int, s_x: torch.Tensor, s_w: torch.Tensor
     pa = (ctypes.c_void_p * len(part_ptrs))(*[ctypes.c_void_p(int(p)) for p in part_ptrs])
     da = (ctypes.c_void_p * len(dest_ptrs))(*[ctypes.c_void_p(int(p)) for p in dest_ptrs])
     if M and N:
-        _lib.check(_lib.lib().pq_reduce_dequant(pa, len(part_ptrs), ld_part, s_x.data_ptr(), s_w.data_ptr(),
-                                                bias.data_ptr() if bias is not None else None, da, len(dest_ptrs),
-                                                _DT[out_dtype], ldy, M, N, _stream()), "pq_reduce_dequant")
+        with _on(s_x, s_w, bias):
+            rc = _lib.lib().pq_reduce_dequant(pa, len(part_ptrs), ld_part, s_x.data_ptr(), s_w.data_ptr(),
+                                              bias.data_ptr() if bias is not None else None, da, len(dest_ptrs),
+                                              _DT[out_dtype], ldy, M, N, _stream(s_x.device))
+        _lib.check(rc, "pq_reduce_dequant")
 
 
 def dequant_accumulators(acc: torch.Tensor, s_x: torch.Tensor, s_w: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -306,10 +374,11 @@ def norm_quant(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
         raise ValueError("norm weight / bias must have K elements")
     xq, s_x, y = _fused_out(M, K, x2, return_normed, out)
     if M:
-        rc = _lib.lib().pq_norm_quant(x2.data_ptr(), _DT[x2.dtype], M, K, x2.stride(0), w.data_ptr(),
-                                      b.data_ptr() if b is not None else None, float(eps),
-                                      xq.data_ptr(), xq.stride(0), s_x.data_ptr(),
-                                      y.data_ptr() if y is not None else None, K, _specp(spec), _stream())
+        with _on(x2, w, b, xq, s_x):
+            rc = _lib.lib().pq_norm_quant(x2.data_ptr(), _DT[x2.dtype], M, K, x2.stride(0), w.data_ptr(),
+                                          b.data_ptr() if b is not None else None, float(eps),
+                                          xq.data_ptr(), xq.stride(0), s_x.data_ptr(),
+                                          y.data_ptr() if y is not None else None, K, _specp(spec), _stream(x2.device))
         _lib.check(rc, "pq_norm_quant")
     return (xq, s_x, y.reshape(x.shape)) if return_normed else (xq, s_x)
 
@@ -348,10 +417,11 @@ def act_mul_quant(gate: torch.Tensor, up: Optional[torch.Tensor] = None, act: st
     M = g2.shape[0]
     hq, s_h, h = _fused_out(M, K, g2, return_float, out)
     if M:
-        rc = _lib.lib().pq_act_mul_quant(g2.data_ptr(), u2.data_ptr() if u2 is not None else None, _DT[g2.dtype],
-                                         _ACTS[act], M, K, g2.stride(0), u2.stride(0) if u2 is not None else 0,
-                                         hq.data_ptr(), hq.stride(0), s_h.data_ptr(),
-                                         h.data_ptr() if h is not None else None, K, _specp(spec), _stream())
+        with _on(g2, u2, hq, s_h):
+            rc = _lib.lib().pq_act_mul_quant(g2.data_ptr(), u2.data_ptr() if u2 is not None else None, _DT[g2.dtype],
+                                             _ACTS[act], M, K, g2.stride(0), u2.stride(0) if u2 is not None else 0,
+                                             hq.data_ptr(), hq.stride(0), s_h.data_ptr(),
+                                             h.data_ptr() if h is not None else None, K, _specp(spec), _stream(g2.device))
         _lib.check(rc, "pq_act_mul_quant")
     return (hq, s_h, h.reshape(gate.shape)) if return_float else (hq, s_h)
 
@@ -375,7 +445,8 @@ def dequantize(q: torch.Tensor, s: torch.Tensor, axis: int = 0, out_dtype: torch
         raise TypeError("s must be contiguous fp32 with one entry per slice along `axis`")
     out = torch.empty((rows, cols), dtype=out_dtype, device=q.device)
     if rows and cols:
-        rc = _lib.lib().pq_dequant(q.data_ptr(), q.stride(0), s.data_ptr(), axis, out.data_ptr(), _DT[out_dtype],
-                                   out.stride(0), rows, cols, _stream())
+        with _on(q, s):
+            rc = _lib.lib().pq_dequant(q.data_ptr(), q.stride(0), s.data_ptr(), axis, out.data_ptr(), _DT[out_dtype],
+                                       out.stride(0), rows, cols, _stream(q.device))
         _lib.check(rc, "pq_dequant")
     return out

@@ -35,6 +35,33 @@ class DynamicQuantLinear(nn.Module):
         else:
             self.bias = None
 
+    # buffers whose dtype is part of the kernel ABI: module.half() / .to(torch.bfloat16) / model.to(dtype) must not
+    # cast them (the C entry points read weight_scale and bias as fp32 through raw pointers)
+    _FP32_BUFFERS = ("weight_scale", "bias")
+
+    def _apply(self, fn, recurse=True):
+        keep = {name: self._buffers.get(name) for name in self._FP32_BUFFERS}
+        super()._apply(fn, recurse)
+        for name, old in keep.items():
+            buf = self._buffers.get(name)
+            if old is not None and buf is not None and buf.dtype != torch.float32:
+                # a dtype cast: keep the ORIGINAL fp32 values (a round trip through fp16 would change them), follow the device
+                self._buffers[name] = old.to(device=buf.device)
+        return self
+
+    def _check_abi_buffers(self, device):
+        """The lean path hands raw pointers to the C ABI: they must be fp32, contiguous and on the input's device."""
+        for name in self._FP32_BUFFERS:
+            buf = getattr(self, name)
+            if buf is None:
+                continue
+            if buf.dtype != torch.float32 or not buf.is_contiguous() or buf.device != device:
+                raise TypeError(f"DynamicQuantLinear.{name} must be a contiguous fp32 tensor on {device} "
+                                f"(got {buf.dtype} on {buf.device})")
+        w = self.qweight_storage
+        if w.dtype != torch.int8 or w.device != device or w.stride(1) != 1 or w.stride(0) % 16 or w.data_ptr() % 16:
+            raise TypeError("DynamicQuantLinear.qweight_storage must be int8 on the input's device with 16-byte aligned rows")
+
     @property
     def qweight(self) -> torch.Tensor:
         """int8 [N, K] view whose row stride is a multiple of 16 bytes."""
@@ -91,6 +118,7 @@ class DynamicQuantLinear(nn.Module):
         if out_dtype not in F._DT:
             raise TypeError(f"unsupported output dtype {out_dtype}")
         wq = self.qweight_storage
+        self._check_abi_buffers(x.device)
         y = torch.empty((M, N), dtype=out_dtype, device=x.device)
         if M:
             xq = torch.empty((M, wq.shape[1]), dtype=torch.int8, device=x.device)
@@ -130,13 +158,140 @@ def fuse_linears(mods) -> DynamicQuantLinear:
     return fused
 
 
+class _SharedInputGroup:
+    """Run-time state of several linears that read the SAME activation (q/k/v, gate/up): their weights live in one
+    fused DynamicQuantLinear, so the activation is quantised once and one GEMM produces every member's output.
+
+    The first member called with an input x runs the fused forward and the result is kept until every member has
+    taken its slice (or another input arrives).  "Same input" = same storage address, tensor version, shape,
+    strides, dtype and CUDA stream; the group holds a reference to x meanwhile, so the address cannot be recycled.
+    A member that arrives with a different input computes only its own slice (one act-quant + one GEMM on its rows
+    of the fused weight); after `MAX_DIVERGENT` such calls the group stops fusing (e.g. cross-attention, where
+    q and k/v read different tensors)."""
+
+    MAX_DIVERGENT = 4
+
+    def __init__(self, fused: DynamicQuantLinear, sizes):
+        self.fused = fused
+        self.bounds = []
+        lo = 0
+        for n in sizes:
+            self.bounds.append((lo, lo + n))
+            lo += n
+        self.all_mask = (1 << len(sizes)) - 1
+        self.divergent = 0
+        self._key = None
+        self._x = None
+        self._y = None
+        self._served = 0
+
+    @staticmethod
+    def _key_of(x: torch.Tensor):
+        return (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.dtype, x.device,
+                torch.cuda.current_stream(x.device).cuda_stream if x.is_cuda else 0)
+
+    def _slice_forward(self, x, idx):
+        lo, hi = self.bounds[idx]
+        f = self.fused
+        bias = f.bias[lo:hi] if f.bias is not None else None
+        return F.qlinear(x, f.qweight[lo:hi], f.weight_scale[lo:hi], bias, f.out_dtype or x.dtype, f.spec)
+
+    def output_for(self, x: torch.Tensor, idx: int) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor) or self.divergent >= self.MAX_DIVERGENT:
+            return self._slice_forward(x, idx)
+        key = self._key_of(x)
+        bit = 1 << idx
+        if self._key == key and not (self._served & bit):
+            y = self._y
+        elif self._key is not None and self._served and self._served != self.all_mask and self._key != key:
+            # the group is in the middle of serving another input: this member reads a different tensor
+            self.divergent += 1
+            return self._slice_forward(x, idx)
+        else:
+            y = self.fused(x)
+            self._key, self._x, self._y, self._served = key, x, y, 0
+        self._served |= bit
+        lo, hi = self.bounds[idx]
+        out = y[..., lo:hi]
+        if self._served == self.all_mask:
+            self._key = self._x = self._y = None
+            self._served = 0
+        return out
+
+
+class SharedInputLinear(nn.Module):
+    """One member (e.g. `k_proj`) of a group of linears fused by `swap_linear(fuse_shared_inputs=True)`.  The fused
+    parameters are registered once, on the parent module (`<parent>._pq_fused_<first member>`); this module only
+    knows its group and its position, and returns its column slice of the fused output (a view: rows keep the fused
+    row stride).  Bit-identical to the separate DynamicQuantLinear: per-output-channel scales make the column
+    blocks of the fused GEMM independent."""
+
+    def __init__(self, group: _SharedInputGroup, index: int, in_features: int, out_features: int):
+        super().__init__()
+        object.__setattr__(self, "_group", group)      # not a registered submodule: the parent owns the parameters
+        self.index = index
+        self.in_features = in_features
+        self.out_features = out_features
+
+    @property
+    def fused(self) -> DynamicQuantLinear:
+        return self._group.fused
+
+    def forward(self, x) -> torch.Tensor:
+        return self._group.output_for(x, self.index)
+
+    def extra_repr(self) -> str:
+        lo, hi = self._group.bounds[self.index]
+        return f"in_features={self.in_features}, out_features={self.out_features}, rows [{lo}, {hi}) of the fused int8 weight"
+
+
+# sibling linears that read the same activation in the common transformer blocks
+SHARED_INPUT_PATTERNS = (
+    ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"),          # Llama / Mistral / Qwen (HF naming)
+    ("query", "key", "value"),                                         # BERT self-attention
+    ("wq", "wk", "wv"), ("w1", "w3"),                                  # Meta Llama naming
+    ("q_lin", "k_lin", "v_lin"),                                       # DistilBERT
+)
+
+
+def _fuse_group(parent: nn.Module, names, out_dtype, spec) -> bool:
+    lins = [getattr(parent, n, None) for n in names]
+    if not all(isinstance(l, nn.Linear) for l in lins):
+        return False
+    k = lins[0].in_features
+    if any(l.in_features != k or (l.bias is None) != (lins[0].bias is None) or l.weight.device != lins[0].weight.device
+           or l.weight.dtype != lins[0].weight.dtype for l in lins):
+        return False
+    fused = fuse_linears([DynamicQuantLinear.from_float(l, out_dtype=out_dtype, spec=spec) for l in lins])
+    group = _SharedInputGroup(fused, [l.out_features for l in lins])
+    setattr(parent, "_pq_fused_" + names[0], fused)
+    for i, (n, l) in enumerate(zip(names, lins)):
+        setattr(parent, n, SharedInputLinear(group, i, k, l.out_features))
+    return True
+
+
 def swap_linear(model: nn.Module, min_features: int = 0, out_dtype: Optional[torch.dtype] = None,
-                spec: Optional[F.QuantSpec] = None, skip=()) -> nn.Module:
-    """Replace every nn.Linear (in/out features >= min_features, name not in `skip`) in place."""
+                spec: Optional[F.QuantSpec] = None, skip=(), fuse_shared_inputs: bool = True,
+                patterns=SHARED_INPUT_PATTERNS) -> nn.Module:
+    """Replace every nn.Linear (in/out features >= min_features, name not in `skip`) in place.
+
+    With `fuse_shared_inputs` (default) sibling linears that read the same activation -- `patterns`, e.g.
+    q_proj/k_proj/v_proj and gate_proj/up_proj -- are fused: the activation is quantised ONCE and one GEMM computes
+    all of them (SharedInputLinear).  The outputs are bit-identical to separate modules; a Llama block then runs 4
+    quantising launches and 4 GEMMs instead of 7 + 7."""
+    if fuse_shared_inputs:
+        for names in patterns:
+            if any(n in skip for n in names):
+                continue
+            lins = [getattr(model, n, None) for n in names]
+            if all(isinstance(l, nn.Linear) and min(l.in_features, l.out_features) >= min_features for l in lins):
+                _fuse_group(model, names, out_dtype, spec)
     for name, child in list(model.named_children()):
+        if isinstance(child, (DynamicQuantLinear, SharedInputLinear)):
+            continue
         if isinstance(child, nn.Linear) and name not in skip and \
                 min(child.in_features, child.out_features) >= min_features:
             setattr(model, name, DynamicQuantLinear.from_float(child, out_dtype=out_dtype, spec=spec))
         else:
-            swap_linear(child, min_features, out_dtype, spec, skip)
+            swap_linear(child, min_features, out_dtype, spec, skip, fuse_shared_inputs, patterns)
     return model

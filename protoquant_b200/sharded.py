@@ -12,8 +12,9 @@ The gather is the path's only exchange step.  Two implementations:
   into ALL ranks' buffers -- one coalesced NVLink peer store per rank (or, opt-in with
   PQ_USE_MULTICAST=1, a single store to the NVSwitch multicast address) -- so the transfer overlaps the MMAs tile
   by tile and no separate collective or layout-fixing copy runs.  One symmetric-memory barrier
-  follows the kernel.  Output buffers are double-buffered: the tensor returned by forward() is
-  valid until the next-but-one forward() of the same module.
+  follows the kernel.  Output buffers are double-buffered: the tensor returned by forward() is a view
+  that stays valid until the next-but-one forward() of the same module (`copy_output=True` returns a
+  private copy instead).
 * NCCL all-gather of the [tokens, N/G] slices (baseline; also the gloo path used by CPU tests).
 
 `min_out_features` implements the north star's "used only for layers big enough to benefit":
@@ -21,6 +22,7 @@ smaller layers stay replicated.
 """
 from __future__ import annotations
 
+import logging
 import os
 from typing import Callable, Optional
 
@@ -29,6 +31,17 @@ import torch.distributed as dist
 from torch import nn
 
 from . import functional as F
+
+log = logging.getLogger("protoquant_b200.sharded")
+
+
+def _agree(ok: bool, device, group) -> bool:
+    """All ranks of `group` learn whether EVERY rank succeeded (MIN all-reduce of a flag): a rank-local failure of
+    the symmetric-memory setup must flip every rank to the fallback together, or the job hangs with some ranks in
+    a symmetric-memory barrier and others in an NCCL collective."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
 
 
 def shard_bounds(n: int, world: int, rank: int, align: int = 8):
@@ -45,7 +58,7 @@ class ShardedDynamicQuantLinear(nn.Module):
                  bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,
                  spec: Optional[F.QuantSpec] = None,
                  local_forward: Optional[Callable] = None, fused: Optional[bool] = None,
-                 gather_output: bool = True, align: int = 8):
+                 gather_output: bool = True, align: int = 8, copy_output: bool = False):
         """qweight_full [N,K] int8, weight_scale_full [N] fp32, bias_full [N] fp32|None: the
         UNSHARDED quantised weight (every rank passes the same tensors; each keeps its slice).
         `local_forward(x2d, wq, s_w, bias, out_dtype)` defaults to the CUDA path; tests on a
@@ -60,7 +73,10 @@ class ShardedDynamicQuantLinear(nn.Module):
         self._local_forward = local_forward
         # fused epilogue all-gather needs CUDA + symmetric memory; None = try it, fall back to NCCL
         self.fused = fused
+        self.fused_error = None   # why the fused path was turned off (repr of the setup exception), if it was
+        self.copy_output = copy_output
         self._symm = None      # (capacity_rows, dtype) -> [(tensor, handle), (tensor, handle)]
+        self._ws = None        # act-quant workspace (xq, s_x) reused across calls
         self._flip = 0
         # gather_output=False keeps the [tokens, hi-lo] slice local (it feeds a row-parallel layer, §8f-3)
         self.gather_output = gather_output
@@ -109,27 +125,62 @@ class ShardedDynamicQuantLinear(nn.Module):
         self._symm = (key, cap, bufs)
         return bufs
 
+    def _enable_fused(self, rows: int, dtype, device) -> bool:
+        """Set up (or grow) the symmetric output buffers.  Only THIS step may fail softly -- symmetric memory can
+        be unavailable -- and the ranks agree on the outcome, so they all take the same path; the reason is kept
+        in `fused_error` and logged once.  Errors of the kernels themselves are never swallowed."""
+        if self._symm is not None and self._symm[0] == (dtype,) and self._symm[1] >= rows:
+            return True
+        err = None
+        try:
+            self._symm_buffers(rows, dtype, device)
+        except Exception as ex:        # noqa: BLE001 - any setup failure means "no symmetric memory here"
+            err = ex
+        group = self.group if self.group is not None else dist.group.WORLD
+        if _agree(err is None, device, group):
+            return True
+        self._symm = None
+        self.fused_error = repr(err) if err is not None else "symmetric-memory setup failed on another rank"
+        if self.fused is True:
+            raise RuntimeError(f"fused epilogue all-gather was requested (fused=True) but is unavailable: {self.fused_error}")
+        log.warning("ShardedDynamicQuantLinear: fused epilogue all-gather unavailable (%s); using the NCCL all-gather",
+                    self.fused_error)
+        self.fused = False
+        return False
+
+    def _workspace(self, rows: int, device):
+        if self._ws is None or self._ws[0].shape[0] < rows or self._ws[0].device != device:
+            kp = self.qweight_storage.shape[1]
+            self._ws = (torch.empty((max(rows, 16), kp), dtype=torch.int8, device=device),
+                        torch.empty((max(rows, 16),), dtype=torch.float32, device=device))
+        return self._ws
+
     def _forward_fused(self, x2: torch.Tensor, out_dtype) -> torch.Tensor:
         M = x2.shape[0]
-        bufs = self._symm_buffers(M, out_dtype, x2.device)
+        bufs = self._symm[2]
         t, h = bufs[self._flip]
         self._flip ^= 1
         esz = t.element_size()
         ld = self.world * self.per
         off = self.rank * self.per * esz
         mc = int(getattr(h, "multicast_ptr", 0) or 0) if getattr(h, "has_multicast_support", False) else 0
-        # Measured on 2 x B200 (profiles/README_r1.md): per-peer NVLink stores 0.22 ms vs one store to the
-        # NVSwitch multicast address 0.90 ms for the 2048 x 28672 output, so multicast is opt-in.
-        if mc and os.environ.get("PQ_USE_MULTICAST"):
-            dests = [mc + off]
-        else:
-            dests = [int(p) + off for p in h.buffer_ptrs]
-        xq, s_x = F.quantize_act(x2, spec=self.spec)
-        F.qgemm_multi(xq, s_x, self.qweight, self.weight_scale, self.bias, dests, ld, out_dtype)
+        # PQ_USE_MULTICAST=1: one multimem.st per 16 bytes to the NVSwitch multicast address (the switch replicates
+        # it into every rank); default: one TMA bulk store per destination (local buffer + each peer over NVLink).
+        multicast = bool(mc and os.environ.get("PQ_USE_MULTICAST"))
+        dests = [mc + off] if multicast else [int(p) + off for p in h.buffer_ptrs]
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        xq_ws, sx_ws = self._workspace(M, x2.device)
+        F.qlinear_multi_into(x2, self.qweight_storage, self.in_features, self.weight_scale, self.bias, dests, ld,
+                             out_dtype, xq_ws, sx_ws, self.spec, multicast=multicast)
         h.barrier()
-        return t[:M, : self.out_features]
+        y = t[:M, : self.out_features]
+        return y.clone() if self.copy_output else y
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [..., K] (replicated) -> y [..., N] (gathered).  On the fused path the result is a VIEW into a
+        double-buffered symmetric-memory buffer: it is overwritten by the second forward() after this one
+        (construct with copy_output=True to get a private tensor)."""
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         out_dtype = self.out_dtype or x.dtype
@@ -137,14 +188,9 @@ class ShardedDynamicQuantLinear(nn.Module):
             y_local = self.local(x2, out_dtype)
             return y_local[:, : self.hi - self.lo].reshape(*lead, self.hi - self.lo)
         if self.world > 1 and self._local_forward is None and x2.is_cuda and self.fused is not False:
-            try:
-                y = self._forward_fused(x2, out_dtype)
+            if self._enable_fused(x2.shape[0], out_dtype, x2.device):
                 self.fused = True
-                return y.reshape(*lead, self.out_features)
-            except Exception:
-                if self.fused is True:
-                    raise
-                self.fused = False       # symmetric memory unavailable: NCCL all-gather from now on
+                return self._forward_fused(x2, out_dtype).reshape(*lead, self.out_features)
         y_local = self.local(x2, out_dtype).contiguous()          # [M, per]
         if self.world == 1:
             return y_local[:, : self.out_features].reshape(*lead, self.out_features)
@@ -196,6 +242,7 @@ class RowParallelDynamicQuantLinear(nn.Module):
         self.gather_output = gather_output
         self.ops = ops or _CudaShardOps
         self.fused = fused
+        self.fused_error = None
         self._symm = None
         self._flip = 0
         self.k_lo, self.k_hi = shard_bounds(self.in_features, self.world, self.rank, align=16)
@@ -242,8 +289,29 @@ class RowParallelDynamicQuantLinear(nn.Module):
         self._symm = (key, cap, bufs)
         return cap, bufs
 
+    def _enable_fused(self, rows: int, dtype, device) -> bool:
+        """Symmetric-memory setup: the only step that may fail softly; all ranks agree on the outcome."""
+        if self._symm is not None and self._symm[0] == (dtype,) and self._symm[1] >= rows:
+            return True
+        err = None
+        try:
+            self._symm_buffers(rows, dtype, device)
+        except Exception as ex:        # noqa: BLE001
+            err = ex
+        group = self.group if self.group is not None else dist.group.WORLD
+        if _agree(err is None, device, group):
+            return True
+        self._symm = None
+        self.fused_error = repr(err) if err is not None else "symmetric-memory setup failed on another rank"
+        if self.fused is True:
+            raise RuntimeError(f"fused reduce-scatter was requested (fused=True) but is unavailable: {self.fused_error}")
+        log.warning("RowParallelDynamicQuantLinear: fused reduce-scatter unavailable (%s); using the int32 all-reduce",
+                    self.fused_error)
+        self.fused = False
+        return False
+
     def _forward_fused(self, xq, s_x, M: int, out_dtype) -> torch.Tensor:
-        cap, bufs = self._symm_buffers(M, out_dtype, xq.device)
+        cap, bufs = self._symm[1], self._symm[2]
         inbox, hi, out, ho = bufs[self._flip]
         self._flip ^= 1
         slot = cap * self.per_n * 4                      # bytes of one source rank's inbox
@@ -267,6 +335,8 @@ class RowParallelDynamicQuantLinear(nn.Module):
         return out[:M, : self.out_features]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """With `gather_output` on the fused path the result is a VIEW into a double-buffered symmetric-memory
+        buffer, overwritten by the second forward() after this one; clone it to keep it longer."""
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         out_dtype = self.out_dtype or x.dtype
@@ -274,14 +344,9 @@ class RowParallelDynamicQuantLinear(nn.Module):
         M = x2.shape[0]
         n_out = self.out_features if (self.gather_output or self.world == 1) else self.n_hi - self.n_lo
         if self.world > 1 and self.ops is _CudaShardOps and x2.is_cuda and self.fused is not False:
-            try:
-                y = self._forward_fused(xq, s_x, M, out_dtype)
+            if self._enable_fused(M, out_dtype, xq.device):
                 self.fused = True
-                return y.reshape(*lead, n_out)
-            except Exception:
-                if self.fused is True:
-                    raise
-                self.fused = False
+                return self._forward_fused(xq, s_x, M, out_dtype).reshape(*lead, n_out)
         acc = self.ops.int_mm(xq, self.qweight)              # exact int32 partial sums of this K-slice
         if self.world > 1:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
@@ -333,9 +398,34 @@ class ParallelGatedMLP(nn.Module):
         return y.reshape(*lead, self.down.out_features)
 
 
-def maybe_shard(linear_q, group=None, min_out_features: int = 16384, **kw):
-    """Shard a DynamicQuantLinear across `group` only if it is big enough to benefit."""
+class TokenAdaptiveLinear(nn.Module):
+    """Keeps the replicated DynamicQuantLinear next to its column-sharded twin and picks per call by token count:
+    calls with fewer than `min_tokens` tokens run on the replicated copy.  Round 1 needed this (M = 16 on 8 GPUs:
+    replicated 52 us vs sharded 64-71 us); since round 2 the sharded forward is one C call whose decode kernel writes
+    all destinations itself and wins at every token count measured (profiles/README_r2.md), so `maybe_shard` no
+    longer uses it by default -- it remains for fabrics where the cross-rank barrier is expensive.  The input is
+    replicated, so every rank takes the same branch.  Costs (1 + 1/world) x the layer's int8 weights."""
+
+    def __init__(self, replicated: nn.Module, sharded: nn.Module, min_tokens: int):
+        super().__init__()
+        self.replicated = replicated
+        self.sharded = sharded
+        self.min_tokens = int(min_tokens)
+        self.in_features, self.out_features = sharded.in_features, sharded.out_features
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        tokens = x.numel() // max(1, x.shape[-1])
+        return self.replicated(x) if tokens < self.min_tokens else self.sharded(x)
+
+
+def maybe_shard(linear_q, group=None, min_out_features: int = 16384, min_tokens: int = 0, **kw):
+    """Shard a DynamicQuantLinear across `group` only where that is measured to pay ("used only for layers big
+    enough to benefit"): layers with fewer than `min_out_features` outputs stay replicated, and -- `min_tokens` > 0 --
+    calls with fewer tokens than that run on the replicated copy (TokenAdaptiveLinear)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1 or linear_q.out_features < min_out_features:
         return linear_q
-    return ShardedDynamicQuantLinear(linear_q.qweight, linear_q.weight_scale, linear_q.bias, group=group,
-                                     out_dtype=linear_q.out_dtype, spec=linear_q.spec, **kw)
+    sharded = ShardedDynamicQuantLinear(linear_q.qweight, linear_q.weight_scale, linear_q.bias, group=group,
+                                        out_dtype=linear_q.out_dtype, spec=linear_q.spec, **kw)
+    if min_tokens > 0:
+        return TokenAdaptiveLinear(linear_q, sharded, min_tokens)
+    return sharded

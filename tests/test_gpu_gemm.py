@@ -252,6 +252,54 @@ def test_qgemm_multi_writes_every_destination_slice():
         assert not b[:, :off].any() and not b[:, off + N:].any()
 
 
+@pytest.mark.parametrize("tma", [2, 1, 0])
+@pytest.mark.parametrize("shape", [(300, 512, 256), (2048, 3584, 1024), (129, 200, 384), (70, 72, 128), (1000, 1000, 512),
+                                   (16, 3584, 1024), (1, 264, 4096), (64, 520, 136)])
+def test_qgemm_multi_tma_and_lsu_destinations_agree(shape, tma):
+    """The multi-destination epilogue (fused all-gather) in its three forms -- 2: per-warp TMA boxes with the regular
+    tile heuristic, 1: CTA-staged tile + TMA stores, 0: CTA-staged tile + LSU copy-out (default: fastest over NVLink);
+    M <= 64 takes the weight-streaming kernel, which writes its rows to every destination itself -- every destination
+    gets the bits of the single-destination GEMM;
+    rows past M and columns outside the slice stay untouched (ragged M / N exercise the tensor-map clipping)."""
+    from protoquant_b200 import functional as F
+    M, N, K = shape
+    N_total, off = N + 2 * 264, 264
+    g = torch.Generator().manual_seed(51)
+    xq, wq = rand_i8((M, K), 52).cuda(), rand_i8((N, K), 53).cuda()
+    s_x = (torch.rand(M, generator=g) * 0.1 + 1e-3).cuda()
+    s_w = (torch.rand(N, generator=g) * 0.01 + 1e-4).cuda()
+    ref = pq.qgemm(xq, s_x, wq, s_w, None, torch.bfloat16)
+    bufs = [torch.zeros(M + 3, N_total, dtype=torch.bfloat16, device="cuda") for _ in range(4)]
+    pq.lib().pq_debug_set_multi_tma(tma)
+    try:
+        F.qgemm_multi(xq, s_x, wq, s_w, None, [b.data_ptr() + off * 2 for b in bufs], N_total, torch.bfloat16)
+    finally:
+        pq.lib().pq_debug_set_multi_tma(0)
+    for b in bufs:
+        assert torch.equal(b[:M, off:off + N], ref)
+        assert not b[:, :off].any() and not b[:, off + N:].any() and not b[M:].any()
+
+
+def test_qlinear_multi_one_call_equals_qlinear():
+    """pq_qlinear_multi (act-quant + multi-destination GEMM behind one C call) == pq_qlinear, bit for bit."""
+    from protoquant_b200 import functional as F
+    M, N, K = 257, 1032, 520
+    torch.manual_seed(61)
+    lin = torch.nn.Linear(K, N).to(torch.bfloat16).cuda()
+    m = pq.DynamicQuantLinear.from_float(lin)
+    x = torch.randn(M, K, dtype=torch.bfloat16, device="cuda")
+    ref = m(x)
+    bufs = [torch.zeros(M, N, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    xq_ws = torch.empty(M, m.qweight_storage.shape[1], dtype=torch.int8, device="cuda")
+    sx_ws = torch.empty(M, dtype=torch.float32, device="cuda")
+    before = pq.launch_count()
+    F.qlinear_multi_into(x, m.qweight_storage, K, m.weight_scale, m.bias, [b.data_ptr() for b in bufs], N, torch.bfloat16,
+                         xq_ws, sx_ws)
+    assert pq.launch_count() - before == 2
+    for b in bufs:
+        assert torch.equal(b, ref)
+
+
 @pytest.mark.parametrize("shape", [(1, 4096, 4096), (2, 4096, 4096), (7, 11008, 4096), (16, 4096, 11008), (17, 768, 3072),
                                    (31, 3072, 768), (33, 1000, 144), (64, 4096, 4096), (64, 8192, 8192), (50, 264, 272),
                                    (48, 28672, 8192), (16, 8192, 28672), (5, 8, 16), (16, 136, 4096)])

@@ -100,6 +100,110 @@ def test_fused_linears_equal_the_separate_linears_bit_for_bit():
         assert torch.equal(m(x), y)
 
 
+class _LlamaLikeBlock(nn.Module):
+    def __init__(self, hidden=512, kv=256, inter=1376):
+        super().__init__()
+        self.q_proj = nn.Linear(hidden, hidden, bias=False)
+        self.k_proj = nn.Linear(hidden, kv, bias=False)      # grouped-query attention: narrower k / v
+        self.v_proj = nn.Linear(hidden, kv, bias=False)
+        self.o_proj = nn.Linear(hidden, hidden, bias=False)
+        self.gate_proj = nn.Linear(hidden, inter, bias=False)
+        self.up_proj = nn.Linear(hidden, inter, bias=False)
+        self.down_proj = nn.Linear(inter, hidden, bias=False)
+
+
+def test_swap_linear_quantises_each_shared_activation_once():
+    """swap_linear(fuse_shared_inputs=True) (the default): q/k/v and gate/up share ONE act-quant launch and ONE GEMM,
+    and every member's output has the bits of the separately swapped module."""
+    import copy
+    torch.manual_seed(5)
+    blk = _LlamaLikeBlock().to(torch.bfloat16).cuda()
+    sep = pq.swap_linear(copy.deepcopy(blk), fuse_shared_inputs=False)
+    fus = pq.swap_linear(copy.deepcopy(blk))
+    assert isinstance(fus.q_proj, pq.SharedInputLinear) and isinstance(fus.up_proj, pq.SharedInputLinear)
+    assert isinstance(fus.o_proj, pq.DynamicQuantLinear) and isinstance(sep.q_proj, pq.DynamicQuantLinear)
+    x = torch.randn(3, 50, 512, dtype=torch.bfloat16, device="cuda")
+    before = pq.launch_count()
+    q, k, v = fus.q_proj(x), fus.k_proj(x), fus.v_proj(x)
+    assert pq.launch_count() - before == 2                     # one act-quant + one GEMM for all three
+    for name, y in (("q_proj", q), ("k_proj", k), ("v_proj", v)):
+        assert torch.equal(y, getattr(sep, name)(x)), name
+    before = pq.launch_count()
+    g, u = fus.gate_proj(x), fus.up_proj(x)
+    assert pq.launch_count() - before == 2
+    assert torch.equal(g, sep.gate_proj(x)) and torch.equal(u, sep.up_proj(x))
+    # a second round with a new tensor recomputes; an in-place update of the same tensor is noticed (version counter)
+    x2 = torch.randn_like(x)
+    assert torch.equal(fus.k_proj(x2), sep.k_proj(x2)) and torch.equal(fus.q_proj(x2), sep.q_proj(x2))
+    assert torch.equal(fus.v_proj(x2), sep.v_proj(x2))
+    q_a = fus.q_proj(x).clone()
+    x.mul_(2)
+    assert torch.equal(fus.k_proj(x), sep.k_proj(x))            # not the stale activation
+    assert torch.equal(fus.v_proj(x), sep.v_proj(x)) and torch.equal(fus.q_proj(x), sep.q_proj(x))
+    assert not torch.equal(fus.q_proj(x), q_a)
+    fus.k_proj(x), fus.v_proj(x)
+    # state_dict: the fused parameters are registered once, on the parent
+    sd = fus.state_dict()
+    assert sd["_pq_fused_q_proj.qweight_storage"].shape[0] == 512 + 256 + 256 and "q_proj.qweight_storage" not in sd
+    fus2 = pq.swap_linear(copy.deepcopy(blk))
+    fus2.load_state_dict(sd)
+    assert torch.equal(fus2.v_proj(x2), sep.v_proj(x2))
+
+
+def test_shared_input_group_with_different_inputs_falls_back_to_its_own_slice():
+    """Cross-attention style use: q reads one tensor, k / v another -> every member still returns the right bits."""
+    import copy
+    torch.manual_seed(6)
+    blk = _LlamaLikeBlock().to(torch.bfloat16).cuda()
+    sep = pq.swap_linear(copy.deepcopy(blk), fuse_shared_inputs=False)
+    fus = pq.swap_linear(copy.deepcopy(blk))
+    xa = torch.randn(40, 512, dtype=torch.bfloat16, device="cuda")
+    xb = torch.randn(24, 512, dtype=torch.bfloat16, device="cuda")
+    for _ in range(6):      # more rounds than _SharedInputGroup.MAX_DIVERGENT: the group stops fusing, results stay exact
+        assert torch.equal(fus.q_proj(xa), sep.q_proj(xa))
+        assert torch.equal(fus.k_proj(xb), sep.k_proj(xb))
+        assert torch.equal(fus.v_proj(xb), sep.v_proj(xb))
+
+
+def test_module_dtype_casts_keep_the_fp32_abi_buffers():
+    """module.half() / .to(bfloat16) must not cast weight_scale / bias (read as fp32 by the kernels)."""
+    torch.manual_seed(7)
+    lin = nn.Linear(256, 384).to(torch.bfloat16).cuda()
+    m = pq.DynamicQuantLinear.from_float(lin)
+    x = torch.randn(33, 256, dtype=torch.bfloat16, device="cuda")
+    ref = m(x)
+    net = nn.Sequential(m)
+    net.half()
+    assert m.weight_scale.dtype == torch.float32 and m.bias.dtype == torch.float32 and m.qweight_storage.dtype == torch.int8
+    net.to(torch.bfloat16)
+    assert torch.equal(m(x), ref)
+    m.weight_scale = m.weight_scale.to(torch.float16)            # bypassing _apply: the lean path must refuse, not misread
+    with pytest.raises(TypeError):
+        m(x)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_module_on_a_non_current_device():
+    """weights and input on cuda:1 while cuda:0 is current (single-process model parallelism)."""
+    torch.manual_seed(8)
+    lin = nn.Linear(512, 640).to(torch.bfloat16)
+    x = torch.randn(300, 512, dtype=torch.bfloat16)
+    torch.cuda.set_device(0)
+    m0 = pq.DynamicQuantLinear.from_float(copy_to(lin, "cuda:0"))
+    y0 = m0(x.to("cuda:0"))
+    m1 = pq.DynamicQuantLinear.from_float(copy_to(lin, "cuda:1"))
+    assert torch.cuda.current_device() == 0
+    y1 = m1(x.to("cuda:1"))
+    assert y1.device.index == 1 and torch.equal(y1.cpu(), y0.cpu())
+    with pytest.raises(pq.ProtoquantError):
+        pq.qgemm(*pq.quantize_act(x.to("cuda:1")), m0.qweight, m0.weight_scale)
+
+
+def copy_to(lin, device):
+    import copy
+    return copy.deepcopy(lin).to(device)
+
+
 def test_sharded_module_single_rank_equals_unsharded():
     torch.manual_seed(3)
     lin = nn.Linear(512, 1000).to(torch.bfloat16).cuda()

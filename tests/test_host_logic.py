@@ -210,3 +210,74 @@ def test_row_parallel_gloo_world2_bit_identical(N, K):
 def test_maybe_shard_keeps_small_layers_replicated():
     m = pq.DynamicQuantLinear(64, 32)
     assert pq.maybe_shard(m) is m
+
+
+def test_shared_input_group_cache_logic_with_a_stub_kernel():
+    """The bookkeeping of swap_linear's shared-input fusion, on CPU tensors with a stub in place of the fused module:
+    one fused forward per distinct activation, slices by member, release after the last member, recompute on a new
+    tensor, on an in-place update (version counter) and when one member is called twice."""
+    from protoquant_b200.modules import _SharedInputGroup
+
+    class Stub:
+        calls = 0
+
+        def __call__(self, x):
+            Stub.calls += 1
+            return torch.cat([x[..., :1] * 1.0, x[..., :2] * 2.0, x[..., :3] * 3.0], dim=-1)
+
+    grp = _SharedInputGroup(Stub(), [1, 2, 3])
+    x = torch.arange(12.0).reshape(3, 4)
+    a, b, c = grp.output_for(x, 0), grp.output_for(x, 1), grp.output_for(x, 2)
+    assert Stub.calls == 1 and a.shape == (3, 1) and b.shape == (3, 2) and c.shape == (3, 3)
+    assert torch.equal(b, x[:, :2] * 2.0) and torch.equal(c, x[:, :3] * 3.0)
+    assert grp._x is None and grp._y is None                     # released after the last member
+    grp.output_for(x, 0)
+    assert Stub.calls == 2                                        # a new round recomputes
+    grp.output_for(x, 0)
+    assert Stub.calls == 3                                        # the same member twice: not served from the cache
+    grp.output_for(x, 1), grp.output_for(x, 2)
+    assert Stub.calls == 3
+    y = torch.ones(3, 4)
+    grp.output_for(y, 0), grp.output_for(y, 1), grp.output_for(y, 2)
+    assert Stub.calls == 4
+
+
+def test_swap_linear_structure_is_checked_on_cpu_only_for_patterns():
+    """Fusion candidates are found by name and shape; nothing is converted on a CPU-only box (from_float needs CUDA)."""
+    from protoquant_b200.modules import SHARED_INPUT_PATTERNS
+    assert ("q_proj", "k_proj", "v_proj") in SHARED_INPUT_PATTERNS and ("gate_proj", "up_proj") in SHARED_INPUT_PATTERNS
+    blk = torch.nn.Module()
+    blk.q_proj, blk.k_proj, blk.v_proj = (torch.nn.Linear(8, 8) for _ in range(3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pq.swap_linear(blk)
+
+
+def test_dtype_casts_never_touch_the_fp32_abi_buffers():
+    m = pq.DynamicQuantLinear(64, 32)
+    m.weight_scale.fill_(1.2345678e-6)          # not representable in fp16 / bf16: a cast round trip would change it
+    net = torch.nn.Sequential(m, torch.nn.LayerNorm(32))
+    net.half()
+    assert torch.all(m.weight_scale == torch.tensor(1.2345678e-6))
+    assert m.weight_scale.dtype == torch.float32 and m.bias.dtype == torch.float32 and m.qweight_storage.dtype == torch.int8
+    assert net[1].weight.dtype == torch.float16
+    net.to(torch.bfloat16)
+    assert m.weight_scale.dtype == torch.float32
+    net.double()
+    assert m.bias.dtype == torch.float32
+
+
+def test_token_adaptive_linear_dispatches_by_token_count():
+    calls = []
+
+    class Rec(torch.nn.Module):
+        def __init__(self, tag):
+            super().__init__()
+            self.tag, self.in_features, self.out_features = tag, 8, 4
+
+        def forward(self, x):
+            calls.append(self.tag)
+            return x[..., :4]
+
+    m = pq.TokenAdaptiveLinear(Rec("replicated"), Rec("sharded"), min_tokens=128)
+    m(torch.zeros(16, 8)); m(torch.zeros(4, 32, 8)); m(torch.zeros(2, 8, 8))
+    assert calls == ["replicated", "sharded", "replicated"]
