@@ -64,6 +64,20 @@ typedef struct pq_quant_spec {
   int32_t qmin;       /* -128 (default) or -127                                    */
 } pq_quant_spec;
 
+/* Non-finite and denormal input (every quantizing entry point, every dtype, every kernel).
+ * The formula  amax = max|x|,  s = amax/127 (amax == 0 -> 1),  q = clamp(rne(x/s), qmin, 127)  is evaluated
+ * literally in IEEE-754 binary32 arithmetic, with NaN -> 0 at the float -> int8 conversion:
+ *   - amax PROPAGATES NaN and +inf, so a row (token / output channel) holding a NaN gets s = NaN, a row holding
+ *     +-inf (and no NaN) gets s = +inf; in both cases every code of that row is 0 (finite/inf = 0,
+ *     inf/inf = NaN -> 0, x/NaN = NaN -> 0).  Dequantising such a row, or running it through the GEMM epilogue,
+ *     yields NaN (0 * s) -- the non-finite input stays visible downstream; other rows are unaffected;
+ *   - fp32 rows whose amax is so small that s is denormal or underflows to 0 (amax < 127 * 2^-126) keep the clamp
+ *     live: x/0 = +-inf -> 127 / qmin, 0/0 -> 0, and a coarsely rounded denormal s may give |x/s| > 127 -> clamp;
+ *     bf16 / fp16 denormals always have a normal or exactly representable fp32 scale and need no special case;
+ *   - the sign and payload of a NaN scale are unspecified.
+ * tests/test_gpu_quant.py::test_nonfinite_and_denormal_rows_follow_the_policy and the exact-rational golden
+ * vectors (tests/golden/exact_*.npz) pin this for all kernels. */
+
 int pq_version(void);
 const char* pq_last_error(void);
 

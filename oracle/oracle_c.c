@@ -19,7 +19,7 @@ void pqo_quantize_rowwise_f32(const float* x, int64_t rows, int64_t cols, int64_
     float amax = 0.f;
     for (int64_t c = 0; c < cols; ++c) {
       float a = fabsf(xr[c]);
-      if (a > amax) amax = a;
+      if (amax == amax && (a != a || a > amax)) amax = a;   /* NaN propagates (and then stays) */
     }
     if (eps > 0.f && amax < eps) amax = eps;
     volatile float s = amax / 127.0f;
@@ -29,6 +29,7 @@ void pqo_quantize_rowwise_f32(const float* x, int64_t rows, int64_t cols, int64_
     for (int64_t c = 0; c < cols; ++c) {
       volatile float t = (scale_mode == 0) ? xr[c] / s : xr[c] * inv;
       float v = nearbyintf(t); /* default rounding mode: half to even */
+      if (v != v) v = 0.f;     /* non-finite policy: NaN -> 0, everything else saturates through the clamp */
       if (v < (float)qmin) v = (float)qmin;
       if (v > 127.f) v = 127.f;
       q[r * ldq + c] = (int8_t)v;
@@ -84,6 +85,7 @@ void pqo_quantize_rowwise_amax_f32(const float* x, int64_t rows, int64_t cols, i
     for (int64_t c = 0; c < cols; ++c) {
       volatile float t = (scale_mode == 0) ? xr[c] / s : xr[c] * inv;
       float v = nearbyintf(t);
+      if (v != v) v = 0.f;
       if (v < (float)qmin) v = (float)qmin;
       if (v > 127.f) v = 127.f;
       q[r * ldq + c] = (int8_t)v;

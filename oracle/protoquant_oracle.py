@@ -15,7 +15,9 @@ against protoquant itself.  What it follows instead:
 * SURVEY.md §8c "SPEC v0" (frozen default, every item a knob):
   upcast to fp32 · amax = max|x| over the last dim · s = amax/127 (fp32 true
   division) · amax == 0 -> s = 1 · q = rne(x / s) · clamp [-128,127] · scales
-  stored fp32 · epilogue ((float(acc)*s_x)*s_w)+bias in fp32, one RNE cast.
+  stored fp32 · epilogue ((float(acc)*s_x)*s_w)+bias in fp32, one RNE cast ·
+  NaN / inf / denormal-scale rows: the same formula evaluated literally in IEEE arithmetic
+  with NaN -> 0 at the int8 conversion (see quantize_rowwise).
 * The nearest *verifiable* definition in this container, a different project:
   ``torch.ao.quantization.fx._decomposed`` ``choose_qparams_per_token`` (:778-810)
   and ``quantize_per_token`` (:930-965).  ``QuantSpec.torch_ao()`` selects the knob
@@ -105,6 +107,13 @@ def quantize_rowwise(x, spec: QuantSpec = SPEC_V0, amax: Optional[np.ndarray] = 
         else:
             raise ValueError(spec.scale_mode)
     q = np.rint(r)  # round half to even
+    # Non-finite policy (SPEC v0 left it "undefined, documented"; this is the documentation): the formula is
+    # evaluated literally in IEEE arithmetic -- amax and s propagate NaN / inf (np.max, np.maximum and the division
+    # do), x/inf = 0, inf/inf = NaN, x/0 = +-inf -- and the float -> int8 conversion maps NaN to 0 (what the
+    # conversion gives on x86 and on the GPU) and saturates everything else through the clamp.  So a row holding
+    # NaN or +-inf gets scale NaN / inf and all-zero codes, and an fp32 row whose scale underflows to 0 (amax <
+    # 127 * 2^-150) gets +-qmax / qmin for its non-zero elements.
+    q = np.where(np.isnan(q), np.float32(0), q)
     q = np.clip(q, spec.qmin, spec.qmax)
     return q.astype(np.int8), s
 

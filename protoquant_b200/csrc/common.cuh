@@ -53,6 +53,9 @@ inline pq_quant_spec resolve_spec(const pq_quant_spec* s) {
   return s ? *s : d;
 }
 
+// what the kernels receive as `scale_mode`: the mode in the low byte, bit 8 = "qmin is -127" (quant_math.cuh make_rowq)
+inline int mode_bits(const pq_quant_spec& s) { return (s.scale_mode & 0xff) | (s.qmin == -127 ? 0x100 : 0); }
+
 inline int dtype_size(int dt) {
   switch (dt) {
     case PQ_F32: return 4;

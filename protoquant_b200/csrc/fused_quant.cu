@@ -87,14 +87,14 @@ __device__ __forceinline__ float row_reduce(float v, float* red /* [ROWS][WPR] *
 #pragma unroll
   for (int o = (TPR < 32 ? TPR : 32) / 2; o > 0; o >>= 1) {
     const float w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = IS_MAX ? fmaxf(v, w) : v + w;
+    v = IS_MAX ? mag_max(v, w) : v + w;      // mag_max: integer max on the bits, NaN propagates
   }
   if (WPR > 1) {
     if ((t & 31) == 0) red[row_in_cta * WPR + (t >> 5)] = v;
     __syncthreads();
     v = red[row_in_cta * WPR];
 #pragma unroll
-    for (int w = 1; w < WPR; ++w) v = IS_MAX ? fmaxf(v, red[row_in_cta * WPR + w]) : v + red[row_in_cta * WPR + w];
+    for (int w = 1; w < WPR; ++w) v = IS_MAX ? mag_max(v, red[row_in_cta * WPR + w]) : v + red[row_in_cta * WPR + w];
   }
   return v;
 }
@@ -142,8 +142,9 @@ __device__ __forceinline__ void emit_row(const uint4 (&v)[VPT], const RowQ& rq, 
     }
   };
   if (rq.path == 0) emit(std::integral_constant<int, 0>{});
+  else if (rq.path == 2) emit(std::integral_constant<int, 2>{});
   else if (rq.path == 1) emit(std::integral_constant<int, 1>{});
-  else emit(std::integral_constant<int, 2>{});
+  else emit(std::integral_constant<int, 3>{});
 }
 
 struct NormArgs {
@@ -490,7 +491,7 @@ extern "C" int pq_norm_quant(const void* x, int x_dtype, int64_t M, int64_t K, i
   NormArgs a;
   a.x = x; a.gamma = gamma; a.beta = beta; a.xq = xq; a.s_out = s_x; a.y = y;
   a.M = M; a.ldx = ldx; a.ldq = ldq; a.ldy = ldy;
-  a.nvec = (int)(K / epv); a.K = (int)K; a.eps = eps; a.scale_mode = spec.scale_mode; a.qeps = spec.eps;
+  a.nvec = (int)(K / epv); a.K = (int)K; a.eps = eps; a.scale_mode = mode_bits(spec); a.qeps = spec.eps;
   cudaStream_t st = (cudaStream_t)stream;
   switch (x_dtype) {
     case PQ_F32: return dispatch_cfg<float, NormLauncher>(a, M, a.nvec, st);
@@ -525,7 +526,7 @@ extern "C" int pq_act_mul_quant(const void* gate, const void* up, int dtype, int
   ActArgs a;
   a.gate = gate; a.up = up; a.hq = hq; a.s_out = s_h; a.h = h;
   a.M = M; a.ldg = ldg; a.ldu = ldu; a.ldq = ldq; a.ldh = ldh;
-  a.nvec = (int)(K / epv); a.act = act; a.scale_mode = spec.scale_mode; a.qeps = spec.eps;
+  a.nvec = (int)(K / epv); a.act = act; a.scale_mode = mode_bits(spec); a.qeps = spec.eps;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case PQ_F32: return dispatch_cfg<float, ActLauncher>(a, M, a.nvec, st);

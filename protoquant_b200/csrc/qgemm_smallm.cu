@@ -414,11 +414,7 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
       float f[EPV];
       unpack<T>(raw, f);
 #pragma unroll
-      for (int j = 0; j < EPV; ++j) {
-        if (rq.path == 0) f[j] = quant_fast(f[j], rq);
-        else if (rq.path == 1) f[j] = quant_div(f[j], rq);
-        else f[j] = quant_mul(f[j], rq);
-      }
+      for (int j = 0; j < EPV; ++j) f[j] = quant_any(f[j], rq);
       const int kl = cv * EPV;                       // k offset inside the slice
       const int kbl = kl >> 7, b = kl & 127;         // k-block, byte inside the 128-byte row
       uint8_t* dst = xs + kbl * (MP * BLOCK_K) + (r >> 3) * 1024 + (r & 7) * 128 + ((((b >> 4) ^ (r & 7))) << 4) + (b & 15);
@@ -707,7 +703,7 @@ int launch_qlinear_smallm_fused(const void* x, int x_dtype, int64_t ldx,
   g.x = x; g.ldx = ldx;
   g.s_w = s_w; g.bias = bias;
   g.out = out; g.ldo = ldo;
-  g.scale_mode = spec.scale_mode; g.eps = spec.eps;
+  g.scale_mode = mode_bits(spec); g.eps = spec.eps;
   switch (x_dtype) {
     case PQ_BF16: return launch_fused_out<__nv_bfloat16>(b, ldb, g, S, out_dtype, stream);
     case PQ_F16: return launch_fused_out<__half>(b, ldb, g, S, out_dtype, stream);

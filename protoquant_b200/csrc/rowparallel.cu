@@ -37,15 +37,15 @@ row_absmax_kernel(const T* __restrict__ x, int64_t K, int64_t ldx, float* __rest
       for (int64_t v = threadIdx.x; v < nvec; v += 256) amax = vec_absmax<float>(ld_stream_16(xr + v * EPV), amax);
     }
   } else {
-    for (int64_t k = threadIdx.x; k < K; k += 256) amax = fmaxf(amax, fabsf((float)xr[k]));
+    for (int64_t k = threadIdx.x; k < K; k += 256) amax = mag_max(amax, mag_of((float)xr[k]));
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  for (int o = 16; o > 0; o >>= 1) amax = mag_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int w = 1; w < 8; ++w) amax = fmaxf(amax, red[w]);
+    for (int w = 1; w < 8; ++w) amax = mag_max(amax, red[w]);
     amax_out[blockIdx.x] = amax;
   }
 }

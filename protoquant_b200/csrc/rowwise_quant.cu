@@ -18,8 +18,9 @@
 // every (amax, x) pair of bf16 and of fp16 inputs with s in [2^-100, 2^100]; rows
 // whose scale falls outside [2^-60, 2^60] take the `div.rn.f32` path instead.
 // The final round-half-even to integer is done with the 1.5*2^23 magic add, whose
-// low mantissa byte is the two's complement int8 (|q1| <= 127.01 always, so the
-// [-128,127] clamp of the reference formula can never fire for finite input).
+// low mantissa byte is the two's complement int8.  On the fast paths |q1| <= 127.01 always, so the
+// [-128,127] clamp of the reference formula cannot fire; rows with a NaN / inf / zero / denormal scale
+// take the "careful" paths of quant_math.cuh, which evaluate the formula literally (clamp live, NaN -> 0).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "quant_math.cuh"
@@ -103,12 +104,12 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
   }
 #pragma unroll
   for (int o = (TPR < 32 ? TPR : 32) / 2; o > 0; o >>= 1)
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    amax = mag_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));   // integer max on the bits: NaN propagates
   if (WPR > 1) {
     if ((t & 31) == 0) red[row_in_cta][t >> 5] = amax;
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < WPR; ++w) amax = fmaxf(amax, red[row_in_cta][w]);
+    for (int w = 0; w < WPR; ++w) amax = mag_max(amax, red[row_in_cta][w]);
   }
   // row-parallel shards quantise a K-slice with the |.|-max of the WHOLE row (pq_act_quant_amax)
   if (amax_in != nullptr && row_ok) amax = __ldg(amax_in + row);
@@ -140,8 +141,9 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
     }
   };
   if (rq.path == 0) emit(std::integral_constant<int, 0>{});
+  else if (rq.path == 2) emit(std::integral_constant<int, 2>{});
   else if (rq.path == 1) emit(std::integral_constant<int, 1>{});
-  else emit(std::integral_constant<int, 2>{});
+  else emit(std::integral_constant<int, 3>{});
 }
 
 // ---- generic kernel: any K / stride / alignment, optional transposed output --------
@@ -161,22 +163,19 @@ rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int6
   const int64_t row = blockIdx.x;
   const T* xr = x + row * ldx;
   float amax = 0.f;
-  for (int64_t k = threadIdx.x; k < K; k += 256) amax = fmaxf(amax, fabsf(load_as_float<T>(xr + k)));
+  for (int64_t k = threadIdx.x; k < K; k += 256) amax = mag_max(amax, mag_of(load_as_float<T>(xr + k)));
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  for (int o = 16; o > 0; o >>= 1) amax = mag_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
   __syncthreads();
 #pragma unroll
-  for (int w = 0; w < 8; ++w) amax = fmaxf(amax, red[w]);
+  for (int w = 0; w < 8; ++w) amax = mag_max(amax, red[w]);
   if (amax_in != nullptr) amax = __ldg(amax_in + row);
   const RowQ rq = make_rowq(amax, scale_mode, eps);
   if (threadIdx.x == 0) s_out[row] = rq.s;
   for (int64_t k = threadIdx.x; k < K; k += 256) {
     const float xv = load_as_float<T>(xr + k);
-    float m;
-    if (rq.path == 0) m = quant_fast(xv, rq);
-    else if (rq.path == 1) m = quant_div(xv, rq);
-    else m = quant_mul(xv, rq);
+    const float m = quant_any(xv, rq);
     if (transpose) xq[k * ldq + row] = code_of(m);
     else xq[row * ldq + k] = code_of(m);
   }
@@ -216,11 +215,11 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
           for (int64_t v = lane; v < nvec; v += 32) amax = vec_absmax<float>(ld_stream_16(xr + v * EPV), amax);
         }
       } else {
-        for (int64_t k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(load_as_float<T>(xr + k)));
+        for (int64_t k = lane; k < K; k += 32) amax = mag_max(amax, mag_of(load_as_float<T>(xr + k)));
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    for (int o = 16; o > 0; o >>= 1) amax = mag_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if (lane == 0) {
       const RowQ rq = make_rowq(amax, scale_mode, eps);
       rowq[r] = rq;
@@ -254,11 +253,7 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
         }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (rq.path == 0) f[j] = quant_fast(f[j], rq);
-        else if (rq.path == 1) f[j] = quant_div(f[j], rq);
-        else f[j] = quant_mul(f[j], rq);
-      }
+      for (int j = 0; j < 16; ++j) f[j] = quant_any(f[j], rq);
       uint4 o;
       o.x = pack4(f[0], f[1], f[2], f[3]);   o.y = pack4(f[4], f[5], f[6], f[7]);
       o.z = pack4(f[8], f[9], f[10], f[11]); o.w = pack4(f[12], f[13], f[14], f[15]);
@@ -296,7 +291,7 @@ int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int6
   constexpr int ROWS = THREADS / TPR;
   const int64_t grid = (M + ROWS - 1) / ROWS;
   PQ_CUDA(launch_pdl(rowwise_quant_vec_kernel<T, TPR, VPT>, (unsigned)grid, THREADS, st,
-                     (const T*)x, M, nvec, ldx, xq, ldq, s, spec.scale_mode, spec.eps,
+                     (const T*)x, M, nvec, ldx, xq, ldq, s, mode_bits(spec), spec.eps,
                      (const uint8_t*)pf, pf_bytes, amax_in));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;
@@ -316,10 +311,10 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
                       (((uintptr_t)xq & 15) == 0) && (ldq % 16 == 0);
     if (tvec)
       PQ_CUDA(launch_pdl(rowwise_quant_transposed_kernel<T, true>, (unsigned)grid, 256u, st,
-                         (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
+                         (const T*)x, M, K, ldx, xq, ldq, s, mode_bits(spec), spec.eps));
     else
       PQ_CUDA(launch_pdl(rowwise_quant_transposed_kernel<T, false>, (unsigned)grid, 256u, st,
-                         (const T*)x, M, K, ldx, xq, ldq, s, spec.scale_mode, spec.eps));
+                         (const T*)x, M, K, ldx, xq, ldq, s, mode_bits(spec), spec.eps));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return PQ_OK;
   }
@@ -329,7 +324,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
                       (K / EPV <= 8192);
   if (!vec_ok) {
     PQ_CUDA(launch_pdl(rowwise_quant_generic_kernel<T>, (unsigned)M, 256u, st,
-                       (const T*)x, M, K, ldx, xq, ldq, s, 0, spec.scale_mode, spec.eps, amax_in));
+                       (const T*)x, M, K, ldx, xq, ldq, s, 0, mode_bits(spec), spec.eps, amax_in));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return PQ_OK;
   }

@@ -35,6 +35,56 @@ class DynamicQuantLinear(nn.Module):
         else:
             self.bias = None
 
+    # ---- serialisation ------------------------------------------------------------------
+    # state_dict(): qweight_storage int8 [N, ld16(K)] (rows padded to 16 bytes), weight_scale fp32 [N], bias fp32 [N].
+    # nn.Module records `_version` in the state_dict metadata; version 1 = this layout.  A checkpoint may also carry
+    # the payload UNPADDED under `qweight` ([N, K], what QTensor.state()["data"] holds) -- it is re-padded on load.
+    _version = 1
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        ver = local_metadata.get("version", 1)
+        if ver is not None and ver > self._version:
+            error_msgs.append(f"{prefix}: checkpoint written by DynamicQuantLinear format {ver}, this build reads <= {self._version}")
+            return
+        key, alt = prefix + "qweight_storage", prefix + "qweight"
+        src = state_dict.get(key, state_dict.get(alt))
+        if src is not None and (alt in state_dict or tuple(src.shape) != tuple(self.qweight_storage.shape)):
+            # unpadded (or differently padded) payload: copy the [N, K] block into this module's padded storage
+            if src.dim() != 2 or src.shape[0] != self.out_features or src.shape[1] < self.in_features or src.dtype != torch.int8:
+                error_msgs.append(f"{prefix}qweight: expected int8 [{self.out_features}, >={self.in_features}], got "
+                                  f"{src.dtype} {tuple(src.shape)}")
+                return
+            state_dict = dict(state_dict)
+            state_dict.pop(alt, None)
+            fixed = torch.zeros_like(self.qweight_storage, device=src.device)
+            fixed[:, : self.in_features].copy_(src[:, : self.in_features])
+            state_dict[key] = fixed
+        for name in self._FP32_BUFFERS:      # scales / bias saved in another float dtype are widened, never narrowed
+            k = prefix + name
+            if k in state_dict and state_dict[k].dtype != torch.float32:
+                state_dict = dict(state_dict)
+                state_dict[k] = state_dict[k].to(torch.float32)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+    def weight_qtensor(self) -> QTensor:
+        """The packed weight as a QTensor (int8 [N, K] payload + per-output-channel scales)."""
+        return QTensor(self.qweight, self.weight_scale, axis=-1, orig_dtype=torch.float32,
+                       orig_shape=(self.out_features, self.in_features))
+
+    @classmethod
+    def from_qtensor(cls, qt: QTensor, bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                     spec: Optional[F.QuantSpec] = None) -> "DynamicQuantLinear":
+        """Build the module from an already-quantised weight (e.g. QTensor.load(path, device))."""
+        if qt.axis != -1 or qt.data.dim() != 2:
+            raise ValueError("the weight QTensor must be [out_features, in_features] with one scale per row")
+        n, k = qt.data.shape
+        m = cls(k, n, bias is not None, device=qt.data.device, out_dtype=out_dtype, spec=spec)
+        m.qweight_storage[:, :k].copy_(qt.data)
+        m.weight_scale.copy_(qt.scale)
+        if bias is not None:
+            m.bias.copy_(bias.to(torch.float32))
+        return m
+
     # buffers whose dtype is part of the kernel ABI: module.half() / .to(torch.bfloat16) / model.to(dtype) must not
     # cast them (the C entry points read weight_scale and bias as fp32 through raw pointers)
     _FP32_BUFFERS = ("weight_scale", "bias")

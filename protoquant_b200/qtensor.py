@@ -49,9 +49,54 @@ class QTensor:
     def int_repr(self) -> torch.Tensor:
         return self.data
 
-    def state(self):
-        return {"data": self.data.contiguous(), "scale": self.scale, "axis": self.axis,
-                "orig_dtype": self.orig_dtype, "orig_shape": self.orig_shape}
+    # ---- serialisation ------------------------------------------------------------------
+    # The reference's own QTensor format cannot be read (REFERENCE ABSENT); this one is versioned so that a
+    # converter can be added when it can.  Only tensors, ints, strings and tuples are stored, so the file loads
+    # with torch.load(weights_only=True).
+    FORMAT = "protoquant_b200.QTensor"
+    FORMAT_VERSION = 1
+
+    def state(self) -> dict:
+        """Plain-dict form: the int8 payload WITHOUT the row padding ([R, C] contiguous), the fp32 scales and the
+        metadata needed to rebuild the tensor."""
+        return {"format": self.FORMAT, "format_version": self.FORMAT_VERSION,
+                "data": self.data.contiguous(), "scale": self.scale.contiguous(), "axis": int(self.axis),
+                "orig_dtype": str(self.orig_dtype).replace("torch.", ""), "orig_shape": tuple(self.orig_shape)}
+
+    @classmethod
+    def from_state(cls, state: dict, device=None) -> "QTensor":
+        """Inverse of `state()`.  The payload is re-laid out with a 16-byte row stride (the GEMM / TMA requirement),
+        on `device` if given (else wherever the stored tensors live).  Raises on a foreign or newer format."""
+        if state.get("format", cls.FORMAT) != cls.FORMAT:
+            raise ValueError(f"not a {cls.FORMAT} state: format={state.get('format')!r}")
+        ver = int(state.get("format_version", 0))        # 0: round-1 state() (torch.dtype object, no version field)
+        if ver > cls.FORMAT_VERSION:
+            raise ValueError(f"QTensor state has format_version {ver}; this build reads <= {cls.FORMAT_VERSION}")
+        data, scale = state["data"], state["scale"]
+        if data.dtype != torch.int8 or data.dim() != 2:
+            raise TypeError("QTensor state: `data` must be a 2-D int8 tensor")
+        axis = int(state["axis"])
+        if axis not in (-1, 0):
+            raise ValueError(f"QTensor state: unsupported axis {axis}")
+        n_scale = data.shape[0] if axis == -1 else data.shape[1]
+        if scale.dtype != torch.float32 or scale.numel() != n_scale:
+            raise TypeError(f"QTensor state: `scale` must be fp32 with {n_scale} entries")
+        od = state["orig_dtype"]
+        orig_dtype = od if isinstance(od, torch.dtype) else getattr(torch, str(od))
+        dev = torch.device(device) if device is not None else data.device
+        q = F.alloc_q(data.shape[0], data.shape[1], dev)
+        q.copy_(data)
+        return cls(q, scale.to(dev).contiguous(), axis, orig_dtype, tuple(state["orig_shape"]))
+
+    def save(self, f) -> None:
+        torch.save(self.state(), f)
+
+    @classmethod
+    def load(cls, f, device=None) -> "QTensor":
+        return cls.from_state(torch.load(f, map_location="cpu" if device is not None else None, weights_only=True), device)
+
+    def to(self, device) -> "QTensor":
+        return self.from_state(self.state(), device)
 
     def __repr__(self):
         return (f"QTensor(shape={self.orig_shape}, dtype=int8, scale=fp32[{self.scale.numel()}], "

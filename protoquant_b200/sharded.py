@@ -53,7 +53,31 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 8):
     return lo, hi
 
 
+def _full_from_state_dict(state_dict, prefix: str, device):
+    """(qweight [N,K] int8, weight_scale [N] fp32, bias [N] fp32 | None) of ONE unsharded DynamicQuantLinear read out
+    of a full-model checkpoint (`prefix` = the module's name + '.'), moved to `device`.  Accepts the padded
+    `qweight_storage` layout and the unpadded `qweight` one (modules.DynamicQuantLinear._load_from_state_dict)."""
+    w = state_dict.get(prefix + "qweight_storage", state_dict.get(prefix + "qweight"))
+    sw = state_dict.get(prefix + "weight_scale")
+    if w is None or sw is None:
+        raise KeyError(f"checkpoint has no '{prefix}qweight_storage' / '{prefix}weight_scale'")
+    if w.dtype != torch.int8 or w.dim() != 2 or sw.numel() != w.shape[0]:
+        raise TypeError(f"'{prefix}qweight_storage' must be int8 [N, K] with one scale per row")
+    b = state_dict.get(prefix + "bias")
+    return (w.to(device), sw.to(device=device, dtype=torch.float32),
+            b.to(device=device, dtype=torch.float32) if b is not None else None)
+
+
 class ShardedDynamicQuantLinear(nn.Module):
+    @classmethod
+    def from_full_state_dict(cls, state_dict, prefix: str = "", in_features: Optional[int] = None, device=None, **kw):
+        """Every rank loads the SAME full (unsharded) checkpoint of a DynamicQuantLinear -- e.g.
+        torch.load(path, map_location="cpu") -- and keeps only its column slice on `device`.
+        `in_features` trims the 16-byte row padding of `qweight_storage` (default: the stored width)."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        w, sw, b = _full_from_state_dict(state_dict, prefix, dev)
+        return cls(w[:, : (in_features or w.shape[1])], sw, b, **kw)
+
     def __init__(self, qweight_full: torch.Tensor, weight_scale_full: torch.Tensor,
                  bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,
                  spec: Optional[F.QuantSpec] = None,
@@ -226,6 +250,14 @@ class RowParallelDynamicQuantLinear(nn.Module):
       kernels and two barriers, no NCCL call on the data path.
     * Fallback (gloo, or no symmetric memory): int32 all-reduce(SUM) of the partial sums + local epilogue.
     """
+
+    @classmethod
+    def from_full_state_dict(cls, state_dict, prefix: str = "", in_features: Optional[int] = None, device=None, **kw):
+        """Every rank loads the same full checkpoint of a DynamicQuantLinear and keeps its K-slice (see
+        ShardedDynamicQuantLinear.from_full_state_dict)."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        w, sw, b = _full_from_state_dict(state_dict, prefix, dev)
+        return cls(w[:, : (in_features or w.shape[1])], sw, b, **kw)
 
     def __init__(self, qweight_full: torch.Tensor, weight_scale_full: torch.Tensor,
                  bias_full: Optional[torch.Tensor], group=None, out_dtype: Optional[torch.dtype] = None,

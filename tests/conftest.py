@@ -31,3 +31,17 @@ def load_golden_x(d):
 def oracle():
     import protoquant_oracle
     return protoquant_oracle
+
+
+EXACT_SPECS = (  # label in exact_*.npz -> (scale_mode, eps, qmin)
+    ("div", 0, 0.0, -128), ("div_qmin127", 0, 0.0, -127), ("rcp_mul_eps1e5", 1, 1e-5, -128), ("inv_scale", 2, 0.0, -128))
+
+
+def same_scales(a, b):
+    """Bit equality of two fp32 scale vectors, except that any NaN equals any NaN (payload and sign of a NaN are
+    not part of the contract: x86, numpy and the GPU produce different quiet NaNs)."""
+    import numpy as np
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    both = np.isnan(a) & np.isnan(b)
+    return bool(np.array_equal(np.where(both, 0, a.view(np.uint32)), np.where(both, 0, b.view(np.uint32))))

@@ -259,3 +259,70 @@ def test_fused_decode_linear_bit_exact(dtype, name, shape):
         pq.lib().pq_debug_set_fused_decode(0)      # default: off (measured slower, see profiles/README_r1.md)
         assert torch.equal(_bits(outs[0].cpu()), _bits(want))
         assert torch.equal(_bits(outs[1].cpu()), _bits(want))
+
+
+def _same_float_bits(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Bit equality except that a NaN equals any NaN (NaN payloads are not part of the contract)."""
+    a, b = a.cpu(), b.cpu()
+    nan = torch.isnan(a) & torch.isnan(b)
+    return bool(torch.equal(torch.where(nan, torch.zeros_like(a), a).view(torch.int16 if a.element_size() == 2 else torch.int32),
+                            torch.where(nan, torch.zeros_like(b), b).view(torch.int16 if b.element_size() == 2 else torch.int32)))
+
+
+@pytest.mark.parametrize("dtype,name", [(torch.bfloat16, "bf16"), (torch.float16, "f16"), (torch.float32, "f32")])
+@pytest.mark.parametrize("M", [8, 200])
+def test_linear_with_nonfinite_tokens_follows_the_policy(dtype, name, M):
+    """A token holding NaN / +-inf gets a NaN / inf scale and zero codes, so its output row is 0 * s_x = NaN (+ bias);
+    every other token of the batch is unaffected and still bit-exact.  Decode kernel (M = 8, both the two-launch and
+    the fused variant) and the large-M kernel (M = 200)."""
+    K, N = 1024, 384
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(M, K, generator=g)
+    x[1, 3] = float("inf")
+    x[2, K - 1] = float("nan")
+    x[5, 17] = float("-inf"); x[5, 18] = float("nan")
+    x = x.to(dtype)
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    wq_o, sw_o = O.quantize_weight(w)
+    lin = pq.DynamicQuantLinear(K, N, bias=True, device="cuda")
+    lin.qweight_storage[:, :K].copy_(torch.from_numpy(wq_o))
+    lin.weight_scale.copy_(torch.from_numpy(sw_o))
+    lin.bias.copy_(bias)
+    with np.errstate(invalid="ignore"):
+        want = O.qlinear(x, wq_o, sw_o, bias.numpy(), out_dtype=name)
+    assert bool(torch.isnan(want[[1, 2, 5]].float()).all()) and not bool(torch.isnan(want[[0, 3, 4, 6, 7]].float()).any())
+    for fused in ((1, 0) if M <= 64 else (0,)):
+        pq.lib().pq_debug_set_fused_decode(fused)
+        try:
+            y = lin(x.cuda())
+        finally:
+            pq.lib().pq_debug_set_fused_decode(0)
+        assert _same_float_bits(y, want), f"fused={fused}"
+
+
+def test_serialisation_roundtrip_keeps_the_bits(tmp_path):
+    """QTensor.save/load and the module's state_dict through torch.save/torch.load reproduce the
+    dequantised tensor and the forward output bit for bit; a full checkpoint loads into the (single-rank) sharded
+    modules with the same result."""
+    torch.manual_seed(3)
+    x = torch.randn(40, 520, dtype=torch.bfloat16, device="cuda")
+    qt = pq.quantize(x)
+    qt.save(tmp_path / "act.pt")
+    back = pq.QTensor.load(tmp_path / "act.pt", device="cuda")
+    assert torch.equal(back.dequantize(), qt.dequantize()) and back.data.is_cuda
+
+    lin = nn.Linear(520, 264).to(torch.bfloat16).cuda()
+    m = pq.DynamicQuantLinear.from_float(lin)
+    y = m(x)
+    torch.save(m.state_dict(), tmp_path / "lin.pt")
+    sd = torch.load(tmp_path / "lin.pt", map_location="cpu", weights_only=True)
+    m2 = pq.DynamicQuantLinear(520, 264, bias=True, device="cuda")
+    m2.load_state_dict(sd)
+    assert torch.equal(_bits(m2(x)), _bits(y))
+    assert torch.equal(_bits(m2(back)), _bits(y))                     # a loaded QTensor is a valid pre-quantised input
+    col = pq.ShardedDynamicQuantLinear.from_full_state_dict(sd, in_features=520)
+    row = pq.RowParallelDynamicQuantLinear.from_full_state_dict(sd, in_features=520)
+    assert torch.equal(_bits(col(x)), _bits(y)) and torch.equal(_bits(row(x)), _bits(y))
+    m3 = pq.DynamicQuantLinear.from_qtensor(pq.QTensor.from_state(m.weight_qtensor().state(), device="cuda"), bias=m.bias)
+    assert torch.equal(_bits(m3(x)), _bits(y))

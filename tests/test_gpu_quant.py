@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, load_golden_x
+from conftest import EXACT_SPECS, GOLDEN, load_golden_x, same_scales
 import protoquant_b200 as pq
 import protoquant_oracle as O
 
@@ -90,6 +90,59 @@ def test_act_quant_matches_committed_golden(path):
     q, s = pq.quantize_act(x.cuda(), spec=pq.QuantSpec(scale_mode=1, eps=1e-5))
     assert np.array_equal(q.cpu().numpy(), d["q"])
     assert np.array_equal(s.cpu().numpy().view(np.uint32), d["s"].view(np.uint32))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "exact_*.npz"))))
+@pytest.mark.parametrize("kernel", ["vec", "generic", "transposed", "given_amax"])
+def test_act_quant_matches_exact_rational_golden(path, kernel):
+    """Default spec (and the other knob sets) against the exact-rational producer, including the NaN / inf /
+    denormal-scale rows, through each quantizer kernel: the register-resident vector kernel, the generic one
+    (misaligned rows), the transposed one and the given-row-maximum variant of the row-parallel path."""
+    d = np.load(path)
+    x = load_golden_x(d)
+    M, K = x.shape
+    for label, mode, eps, qmin in EXACT_SPECS:
+        spec = pq.QuantSpec(scale_mode=mode, eps=eps, qmin=qmin)
+        if kernel == "vec":
+            q, s = pq.quantize_act(x.cuda(), spec=spec)
+        elif kernel == "generic":
+            big = torch.zeros(M, K + 3, dtype=x.dtype)
+            big[:, 1:K + 1] = x                        # rows start at an odd element: no 16-byte alignment
+            q, s = pq.quantize_act(big.cuda()[:, 1:K + 1], spec=spec)
+        elif kernel == "transposed":
+            q, s = pq.quantize_act(x.cuda(), transpose=True, spec=spec)
+            q = q.t()
+        else:
+            amax = pq.row_absmax(x.cuda())
+            q, s = pq.quantize_act_with_amax(x.cuda(), amax, spec=spec)
+        assert np.array_equal(q.cpu().numpy(), d["q_" + label]), (label, kernel)
+        assert same_scales(s.cpu().numpy(), d["s_" + label].view(np.float32)), (label, kernel)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("spec,ospec", SPECS)
+def test_nonfinite_and_denormal_rows_follow_the_policy(dtype, spec, ospec):
+    """+-inf / NaN policy and denormals.  NaN and inf propagate into the row's scale and the row's
+    codes are zero; other rows of the same launch are untouched; denormal rows (fp32: denormal or zero scale) take
+    the literal clamp(rne(x/s)) with NaN -> 0."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(8, 4096, generator=g)
+    x[1, 77] = float("inf")
+    x[2, 4095] = float("-inf")
+    x[3, 0] = float("nan")
+    x[4, 100] = float("nan"); x[4, 200] = float("inf")
+    x = x.to(dtype)
+    if dtype == torch.float32:
+        x[5] = torch.from_numpy((np.arange(4096) % 200).astype(np.uint32).view(np.float32))   # denormals: bit patterns 0..199
+        x[5, 1] = -x[5, 1]
+        x[6] = 0; x[6, 5] = 1.4e-45; x[6, 9] = -2.8e-45                                  # scale underflows to 0
+    q, s = pq.quantize_act(x.cuda(), spec=spec)
+    qo, so = O.quantize_rowwise(x, ospec)
+    assert np.array_equal(q.cpu().numpy(), qo)
+    assert same_scales(s.cpu().numpy(), so)
+    sn = s.cpu().numpy()
+    assert np.isinf(sn[1]) and np.isinf(sn[2]) and np.isnan(sn[3]) and np.isnan(sn[4])
+    assert not q[1:5].any()
 
 
 def test_kat_round_half_even():

@@ -94,6 +94,78 @@ def test_qtensor_metadata():
         pq.quantize(torch.zeros(4, 4, 4), axis=0)
 
 
+# ---- serialisation: metadata and layout handling, CPU only ------------------------------
+def test_qtensor_state_roundtrip_and_versioning(tmp_path):
+    data = F.alloc_q(6, 20, "cpu")                      # padded rows (stride 32)
+    data.copy_(torch.randint(-127, 128, (6, 20), dtype=torch.int8))
+    qt = pq.QTensor(data, torch.rand(6), orig_dtype=torch.bfloat16, orig_shape=(2, 3, 20))
+    st = qt.state()
+    assert st["format"] == "protoquant_b200.QTensor" and st["format_version"] == 1
+    assert st["data"].is_contiguous() and st["data"].shape == (6, 20) and st["orig_dtype"] == "bfloat16"
+    path = tmp_path / "qt.pt"
+    qt.save(path)
+    back = pq.QTensor.load(path)                        # torch.load(weights_only=True): tensors and plain metadata only
+    assert torch.equal(back.data, qt.data) and torch.equal(back.scale, qt.scale)
+    assert back.data.stride(0) % 16 == 0 and back.orig_dtype == torch.bfloat16 and back.shape == (2, 3, 20) and back.axis == -1
+    # a round-1 state (torch.dtype object, no version field) still loads; a newer or foreign format is refused
+    old = {"data": st["data"], "scale": st["scale"], "axis": -1, "orig_dtype": torch.float16, "orig_shape": (6, 20)}
+    assert pq.QTensor.from_state(old).orig_dtype == torch.float16
+    with pytest.raises(ValueError, match="format_version"):
+        pq.QTensor.from_state({**st, "format_version": 99})
+    with pytest.raises(ValueError, match="not a"):
+        pq.QTensor.from_state({**st, "format": "something.else"})
+    with pytest.raises(TypeError):
+        pq.QTensor.from_state({**st, "scale": st["scale"][:3]})
+    # axis = 0: one scale per column
+    qc = pq.QTensor(torch.zeros(4, 8, dtype=torch.int8), torch.ones(8), axis=0)
+    assert pq.QTensor.from_state(qc.state()).scale.numel() == 8
+
+
+def test_module_checkpoint_versions_layouts_and_qtensor_bridge(tmp_path):
+    m = pq.DynamicQuantLinear(100, 24, bias=True)
+    m.qweight_storage[:, :100].copy_(torch.randint(-127, 128, (24, 100), dtype=torch.int8))
+    m.weight_scale.uniform_(0.1, 1.0)
+    m.bias.normal_()
+    path = tmp_path / "lin.pt"
+    torch.save(m.state_dict(), path)
+    sd = torch.load(path, weights_only=True)
+    assert sd._metadata[""]["version"] == 1
+    m2 = pq.DynamicQuantLinear(100, 24, bias=True)
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.qweight_storage, m.qweight_storage) and torch.equal(m2.weight_scale, m.weight_scale)
+    # unpadded payload under `qweight` (what a QTensor stores), scales saved in half precision: re-padded / widened
+    sd_unpadded = {"qweight": m.qweight.contiguous(), "weight_scale": m.weight_scale.double(), "bias": m.bias}
+    m3 = pq.DynamicQuantLinear(100, 24, bias=True)
+    m3.load_state_dict(sd_unpadded)
+    assert torch.equal(m3.qweight, m.qweight) and m3.qweight_storage.stride(0) == 112
+    assert m3.weight_scale.dtype == torch.float32 and torch.equal(m3.weight_scale, m.weight_scale)
+    # wrong shape and a newer format version are load errors, not silent garbage
+    with pytest.raises(RuntimeError, match="qweight"):
+        pq.DynamicQuantLinear(100, 24).load_state_dict({**sd_unpadded, "qweight": m.qweight[:10].contiguous()})
+    newer = m.state_dict()
+    newer._metadata[""]["version"] = 7
+    with pytest.raises(RuntimeError, match="format 7"):
+        pq.DynamicQuantLinear(100, 24).load_state_dict(newer)
+    # QTensor bridge: weight -> QTensor file -> module
+    m.weight_qtensor().save(tmp_path / "w.pt")
+    m4 = pq.DynamicQuantLinear.from_qtensor(pq.QTensor.load(tmp_path / "w.pt"), bias=m.bias)
+    assert torch.equal(m4.qweight, m.qweight) and torch.equal(m4.weight_scale, m.weight_scale) and torch.equal(m4.bias, m.bias)
+
+
+def test_full_checkpoint_into_sharded_modules_single_rank():
+    m = pq.DynamicQuantLinear(96, 40, bias=True)
+    m.qweight_storage.random_(-127, 128)
+    m.weight_scale.uniform_(0.1, 1.0)
+    m.bias.normal_()
+    model_sd = {"mlp.up." + k: v for k, v in m.state_dict().items()}
+    col = pq.ShardedDynamicQuantLinear.from_full_state_dict(model_sd, "mlp.up.", in_features=96, device="cpu")
+    assert torch.equal(col.qweight, m.qweight) and torch.equal(col.weight_scale, m.weight_scale) and torch.equal(col.bias, m.bias)
+    row = pq.RowParallelDynamicQuantLinear.from_full_state_dict(model_sd, "mlp.up.", in_features=96, device="cpu")
+    assert torch.equal(row.qweight, m.qweight) and (row.k_lo, row.k_hi) == (0, 96)
+    with pytest.raises(KeyError):
+        pq.ShardedDynamicQuantLinear.from_full_state_dict(model_sd, "mlp.down.", device="cpu")
+
+
 # ---- world_size 2 over gloo ------------------------------------------------------------
 def _oracle_local(x2, wq, s_w, bias, out_dtype):
     name = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[out_dtype]
@@ -116,6 +188,12 @@ def _worker(rank, world, port, N, K, M, q):
         ok = torch.equal(y, full) and (lin.lo, lin.hi) == (lo, hi) and y.shape == (M, N)
         y3 = lin(x.reshape(2, M // 2, K))
         ok = ok and torch.equal(y3.reshape(M, N), full)
+        # every rank loads the same FULL checkpoint and keeps its slice
+        ref = pq.DynamicQuantLinear(K, N, bias=True)
+        ref.qweight_storage[:, :K].copy_(torch.from_numpy(wq)); ref.weight_scale.copy_(torch.from_numpy(sw)); ref.bias.copy_(b)
+        ck = {"layer." + k: v for k, v in ref.state_dict().items()}
+        lin2 = pq.ShardedDynamicQuantLinear.from_full_state_dict(ck, "layer.", in_features=K, device="cpu", local_forward=_oracle_local)
+        ok = ok and torch.equal(lin2(x), full) and torch.equal(lin2.qweight_storage, lin.qweight_storage)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

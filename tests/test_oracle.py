@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, ROOT, load_golden_x
+from conftest import EXACT_SPECS, GOLDEN, ROOT, load_golden_x, same_scales
 import protoquant_oracle as O
 
 
@@ -27,6 +27,33 @@ def test_oracle_matches_torch_ao_golden(path):
 def test_int_mm_golden(path):
     d = np.load(path)
     assert np.array_equal(O.int_mm(d["a"], d["b"]), d["acc"])
+
+
+# ---- golden vectors of the DEFAULT spec from exact rational arithmetic (tests/golden/make_golden_exact.py) ----
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "exact_*.npz"))))
+def test_oracle_matches_exact_rational_golden(path):
+    """A third, independent producer (integer / Fraction arithmetic only, no hardware fp division or rounding) pins
+    SPEC v0 -- true division, no eps, the product default -- and the other knob sets, including the NaN / inf /
+    denormal-scale rows."""
+    d = np.load(path)
+    x = load_golden_x(d)
+    for label, mode, eps, qmin in EXACT_SPECS:
+        q, s = O.quantize_rowwise(x, O.QuantSpec(scale_mode=mode, eps=eps, qmin=qmin))
+        assert np.array_equal(q, d["q_" + label]), label
+        assert same_scales(s, d["s_" + label].view(np.float32)), label
+
+
+def test_nonfinite_policy_kat():
+    """NaN / inf propagate into the scale; the row's codes are all zero.  A scale that underflows to 0 saturates."""
+    x = np.array([[1.0, -2.0, np.inf, 0.5], [1.0, np.nan, -np.inf, 0.0], [3e-45, -3e-45, 0.0, 1.4e-45]], np.float32)
+    for mode in (O.DIV, O.RCP_MUL, O.INV_SCALE):
+        q, s = O.quantize_rowwise(x, O.QuantSpec(scale_mode=mode))
+        assert np.isinf(s[0]) and s[0] > 0 and np.isnan(s[1])
+        assert not q[0].any() and not q[1].any()
+    q, s = O.quantize_rowwise(x)
+    assert s[2] == 0.0 and q[2].tolist() == [127, -128, 0, 127]
+    q, s = O.quantize_rowwise(x, O.QuantSpec(qmin=-127))
+    assert q[2].tolist() == [127, -127, 0, 127]
 
 
 # ---- hand-derived known answers for SPEC v0 ---------------------------------------------
@@ -114,6 +141,16 @@ def test_numpy_oracle_equals_c_restatement(clib, dtype, mode, eps):
     qc, sc = _c_quant(clib, x32, mode, eps)
     assert np.array_equal(q, qc)
     assert np.array_equal(s.view(np.uint32), sc.view(np.uint32))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "exact_*.npz"))))
+def test_c_restatement_matches_exact_rational_golden(clib, path):
+    d = np.load(path)
+    x32 = np.ascontiguousarray(O.to_f32(load_golden_x(d)))
+    for label, mode, eps, qmin in EXACT_SPECS:
+        q, s = _c_quant(clib, x32, mode, eps, qmin)
+        assert np.array_equal(q, d["q_" + label]), label
+        assert same_scales(s, d["s_" + label].view(np.float32)), label
 
 
 def test_c_int_mm_and_epilogue(clib):
