@@ -176,6 +176,13 @@ __device__ __forceinline__ void tma_load_2d_2sm_mcast(uint32_t dst, const CUtens
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(m), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// 1-D bulk copy global -> this CTA's shared memory (UBLKCP): `bytes` a multiple of 16, both addresses 16-byte
+// aligned; completion is signalled on `bar` as `bytes` transaction bytes.
+__device__ __forceinline__ void bulk_load_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 // Pull `bytes` (multiple of 16) starting at the 16-byte aligned global address `p` into L2.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

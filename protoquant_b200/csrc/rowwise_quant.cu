@@ -24,11 +24,13 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "quant_math.cuh"
+#include "gemm_common.cuh"   // PerDeviceOnce
 #include <type_traits>
 
 namespace pq {
 Knob g_force_tpr{0}, g_force_vpt{0};   // test hook (pq_debug_set_quant_config)
 Knob g_weight_prefetch{1};              // pq_qlinear: the act-quant kernel pulls the weights into L2
+Knob g_quant_staged{0};                 // 0 = heuristic, 1 = always the shared-memory staged kernel, -1 = never
 namespace {
 
 using namespace qmath;
@@ -144,6 +146,125 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
   else if (rq.path == 2) emit(std::integral_constant<int, 2>{});
   else if (rq.path == 1) emit(std::integral_constant<int, 1>{});
   else emit(std::integral_constant<int, 3>{});
+}
+
+// ---- shared-memory staged kernel: one persistent CTA per SM --------------------------------
+// At activation sizes (M x K of a few tens of MB) the register-resident kernel above is bound by latency, not
+// bandwidth: its CTAs form 1.7-2 waves, every CTA runs load -> reduce -> quantise -> store in lock step, and only
+// what fits in registers is in flight.  Here each SM gets ONE 1024-thread CTA that owns rows b, b + grid, ...; a
+// single thread requests ALL of them up front with 1-D bulk copies (cp.async.bulk -> UBLKCP, up to ~220 KB in
+// flight per SM, no registers involved), one mbarrier per slot, and eight 128-thread groups consume rows as they
+// land: |.|-max pass and quantise pass both read the row from shared memory (128 B/clk -- free next to DRAM), codes
+// go out with 8-byte stores.  Slots are refilled as soon as a group has finished with them, so any M works.
+// Same arithmetic (quant_math.cuh) => bit-identical codes and scales.
+constexpr int STG_THREADS = 1024, STG_TPR = 128, STG_GROUPS = STG_THREADS / STG_TPR;
+constexpr int STG_HEADER = 1024;         // mbarriers (8 B x <= 64 slots) + reduction scratch
+constexpr int STG_MAX_SLOTS = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(STG_THREADS, 1)
+rowwise_quant_staged_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t ldx,
+                            int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
+                            int scale_mode, float eps, const uint8_t* __restrict__ pf, long long pf_bytes,
+                            const float* __restrict__ amax_in, int slots) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  extern __shared__ __align__(128) uint8_t stg_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_smem);                       // [slots]
+  float* red = reinterpret_cast<float*>(stg_smem + 8 * STG_MAX_SLOTS);          // [2][GROUPS][4]
+  uint8_t* buf = stg_smem + STG_HEADER;
+  const uint32_t row_bytes = (uint32_t)nvec * 16u;
+  const int tid = threadIdx.x, g = tid / STG_TPR, t = tid % STG_TPR;
+  const int64_t nmine = (M - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;   // rows b, b + grid, ...
+  // `slots` is a multiple of the number of ACTIVE groups (or smaller than STG_GROUPS, then it is that number): the row
+  // that used a slot before row i, i - slots, then belongs to the same group as row i, so a group never waits for
+  // phase p + 1 of a barrier whose phase p is still pending (an mbarrier parity wait cannot tell those apart).
+  const int ngroups = slots < STG_GROUPS ? slots : STG_GROUPS;
+  auto row_of = [&](int64_t i) { return (int64_t)blockIdx.x + i * gridDim.x; };
+
+  if (tid == 0) {
+    for (int s = 0; s < slots; ++s) ptx::mbar_init(ptx::smem_u32(bars + s), 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::griddep_launch_dependents();
+  if (pf != nullptr && tid == 32) {      // weight prefetch for the GEMM that follows (see the kernel above)
+    const long long per = ((pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15LL;
+    long long off = (long long)blockIdx.x * per;
+    const long long end = (off + per < pf_bytes) ? off + per : (pf_bytes & ~15LL);
+    while (off < end) {
+      const uint32_t n = (uint32_t)((end - off < 16384) ? end - off : 16384);
+      ptx::prefetch_l2_bulk(pf + off, n);
+      off += n;
+    }
+  }
+  __syncthreads();
+  ptx::griddep_wait();   // x may be produced, and xq still be read, by the previous kernel
+  if (tid == 0) {
+    const int64_t n0 = nmine < slots ? nmine : slots;
+    for (int64_t i = 0; i < n0; ++i) {
+      const uint32_t bar = ptx::smem_u32(bars + i);
+      ptx::mbar_arrive_expect_tx(bar, row_bytes);
+      ptx::bulk_load_g2s(ptx::smem_u32(buf + (size_t)i * row_bytes), x + row_of(i) * ldx, row_bytes, bar);
+    }
+  }
+  for (int64_t i = g; g < ngroups && i < nmine; i += ngroups) {
+    const int slot = (int)(i % slots);
+    const uint32_t parity = (uint32_t)((i / slots) & 1);
+    const int64_t row = row_of(i);
+    ptx::mbar_wait(ptx::smem_u32(bars + slot), parity);
+    const uint4* rv = reinterpret_cast<const uint4*>(buf + (size_t)slot * row_bytes);
+    // pass 1: |.|-max of the row
+    float amax = 0.f;
+    if (sizeof(T) == 2) {
+      uint32_t m = 0;
+      for (int v = t; v < nvec; v += STG_TPR) m = absmax_u16x2(rv[v], m);
+      amax = u16_mag_to_float<T>(m);
+    } else {
+      for (int v = t; v < nvec; v += STG_TPR) amax = vec_absmax<float>(rv[v], amax);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = mag_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float* rr = red + (((i / ngroups) & 1) * STG_GROUPS + g) * 4;        // double-buffered per group
+    if ((t & 31) == 0) rr[t >> 5] = amax;
+    ptx::named_bar_sync(1 + g, STG_TPR);
+    amax = mag_max(mag_max(rr[0], rr[1]), mag_max(rr[2], rr[3]));
+    if (amax_in != nullptr) amax = __ldg(amax_in + row);
+    const RowQ rq = make_rowq(amax, scale_mode, eps);
+    if (t == 0) s_out[row] = rq.s;
+    // pass 2: quantise from shared memory
+    int8_t* qr = xq + row * ldq;
+    auto emit = [&](auto path_tag) {
+      constexpr int PATH = decltype(path_tag)::value;
+#pragma unroll 2
+      for (int v = t; v < nvec; v += STG_TPR) {
+        float f[EPV];
+        unpack<T>(rv[v], f);
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) f[j] = quant_one<PATH>(f[j], rq);
+        if (EPV == 8) {
+          uint2 o;
+          o.x = pack4(f[0], f[1], f[2], f[3]);
+          o.y = pack4(f[4 % EPV], f[5 % EPV], f[6 % EPV], f[7 % EPV]);
+          *reinterpret_cast<uint2*>(qr + (int64_t)v * 8) = o;
+        } else {
+          *reinterpret_cast<uint32_t*>(qr + (int64_t)v * 4) = pack4(f[0], f[1], f[2], f[3]);
+        }
+      }
+    };
+    if (rq.path == 0) emit(std::integral_constant<int, 0>{});
+    else if (rq.path == 2) emit(std::integral_constant<int, 2>{});
+    else if (rq.path == 1) emit(std::integral_constant<int, 1>{});
+    else emit(std::integral_constant<int, 3>{});
+    // refill the slot with the row that will use it next (uniform across the group)
+    if (i + slots < nmine) {
+      ptx::named_bar_sync(1 + g, STG_TPR);            // every thread of the group is done reading the slot
+      if (t == 0) {
+        const uint32_t bar = ptx::smem_u32(bars + slot);
+        ptx::fence_proxy_async_smem();                // generic-proxy reads before the async-proxy overwrite
+        ptx::mbar_arrive_expect_tx(bar, row_bytes);
+        ptx::bulk_load_g2s(ptx::smem_u32(buf + (size_t)slot * row_bytes), x + row_of(i + slots) * ldx, row_bytes, bar);
+      }
+    }
+  }
 }
 
 // ---- generic kernel: any K / stride / alignment, optional transposed output --------
@@ -298,6 +419,33 @@ int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int6
 }
 
 template <typename T>
+int launch_staged(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int64_t ldq, float* s,
+                  const pq_quant_spec& spec, cudaStream_t st, const void* pf, long long pf_bytes,
+                  const float* amax_in, int num_sms, int slots) {
+  const int dyn = STG_HEADER + slots * nvec * 16;
+  static gemm::PerDeviceOnce once;
+  const cudaError_t e = once.run([&](int*) {
+    return cudaFuncSetAttribute(rowwise_quant_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (e != cudaSuccess) PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(staged quantizer) failed: %s", cudaGetErrorString(e));
+  const unsigned grid = (unsigned)(M < num_sms ? M : num_sms);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(STG_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, rowwise_quant_staged_kernel<T>, (const T*)x, M, nvec, ldx, xq, ldq, s,
+                             mode_bits(spec), spec.eps, (const uint8_t*)pf, pf_bytes, amax_in, slots));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return PQ_OK;
+}
+
+template <typename T>
 int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq,
              float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st,
              const void* pf, long long pf_bytes, const float* amax_in) {
@@ -329,6 +477,30 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
     return PQ_OK;
   }
   const int nvec = (int)(K / EPV);
+  // Activation-sized problems (more rows than one wave of the register kernel can hold, less than a few waves of
+  // streaming) go to the persistent shared-memory staged kernel; see its header comment.  Measured in
+  // tools/quant_cfg.py -> profiles/quant_staged_r2.log.
+  {
+    int num_sms = 0;
+    const int staged = g_quant_staged;
+    if (staged >= 0 && ((uintptr_t)xq % 8 == 0) && (ldq % 8 == 0) && check_device(&num_sms) == PQ_OK) {
+      const long long row_bytes = (long long)nvec * 16;
+      const long long room = 227 * 1024 - STG_HEADER;
+      const long long rows_per_cta = (M + num_sms - 1) / num_sms;
+      long long slots = room / row_bytes;
+      if (slots > rows_per_cta) slots = rows_per_cta;
+      if (slots > STG_MAX_SLOTS) slots = STG_MAX_SLOTS;
+      if (slots > STG_GROUPS) slots -= slots % STG_GROUPS;      // see the kernel: a multiple of the active groups
+      // measured (profiles/quant_staged_r2.log, bf16): wins for long rows at activation sizes (2048 x 11008: 12.5 ->
+      // 11.2 us, 2048 x 8192: 9.9 -> 9.4) and for a few hundred rows (512 x 4096: 3.4 -> 2.5); ties at 2048 x 4096;
+      // loses for short rows (tiny bulk copies) and from ~100 MB on, where the register kernel streams at peak.
+      const long long bytes = M * row_bytes;
+      const bool auto_ok = row_bytes >= 8192 && M >= num_sms &&
+                           ((row_bytes >= 16384 && bytes <= (64LL << 20)) || M <= 1024);
+      if (slots >= 2 && (staged > 0 || auto_ok))
+        return launch_staged<T>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes, amax_in, num_sms, (int)slots);
+    }
+  }
   // Pick (threads per row, vectors per thread): cover the row with as few idle lanes as possible,
   // preferring small thread groups (more rows in flight per SM) and <= 6 vectors per thread.
   static const int kVpt[5] = {4, 3, 6, 2, 8};
@@ -387,3 +559,5 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
 // Test/bench hook: force (threads per row, 16-byte vectors per thread) of the vectorised kernel; 0,0 = heuristic.
 extern "C" void pq_debug_set_quant_config(int tpr, int vpt) { pq::g_force_tpr = tpr; pq::g_force_vpt = vpt; }
 extern "C" void pq_debug_set_weight_prefetch(int on) { pq::g_weight_prefetch = on; }
+// 0 = heuristic, 1 = force the shared-memory staged quantizer wherever it is applicable, -1 = never use it
+extern "C" void pq_debug_set_quant_staged(int mode) { pq::g_quant_staged = mode; }

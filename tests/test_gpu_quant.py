@@ -11,6 +11,7 @@ import torch
 
 from conftest import EXACT_SPECS, GOLDEN, load_golden_x, same_scales
 import protoquant_b200 as pq
+from protoquant_b200 import functional as F
 import protoquant_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -93,7 +94,7 @@ def test_act_quant_matches_committed_golden(path):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "exact_*.npz"))))
-@pytest.mark.parametrize("kernel", ["vec", "generic", "transposed", "given_amax"])
+@pytest.mark.parametrize("kernel", ["vec", "staged", "generic", "transposed", "given_amax"])
 def test_act_quant_matches_exact_rational_golden(path, kernel):
     """Default spec (and the other knob sets) against the exact-rational producer, including the NaN / inf /
     denormal-scale rows, through each quantizer kernel: the register-resident vector kernel, the generic one
@@ -103,8 +104,12 @@ def test_act_quant_matches_exact_rational_golden(path, kernel):
     M, K = x.shape
     for label, mode, eps, qmin in EXACT_SPECS:
         spec = pq.QuantSpec(scale_mode=mode, eps=eps, qmin=qmin)
-        if kernel == "vec":
-            q, s = pq.quantize_act(x.cuda(), spec=spec)
+        if kernel in ("vec", "staged"):
+            pq.lib().pq_debug_set_quant_staged(1 if kernel == "staged" else -1)
+            try:
+                q, s = pq.quantize_act(x.cuda(), spec=spec)
+            finally:
+                pq.lib().pq_debug_set_quant_staged(0)
         elif kernel == "generic":
             big = torch.zeros(M, K + 3, dtype=x.dtype)
             big[:, 1:K + 1] = x                        # rows start at an odd element: no 16-byte alignment
@@ -113,8 +118,8 @@ def test_act_quant_matches_exact_rational_golden(path, kernel):
             q, s = pq.quantize_act(x.cuda(), transpose=True, spec=spec)
             q = q.t()
         else:
-            amax = pq.row_absmax(x.cuda())
-            q, s = pq.quantize_act_with_amax(x.cuda(), amax, spec=spec)
+            amax = F.row_absmax(x.cuda())
+            q, s = F.quantize_act_with_amax(x.cuda(), amax, spec=spec)
         assert np.array_equal(q.cpu().numpy(), d["q_" + label]), (label, kernel)
         assert same_scales(s.cpu().numpy(), d["s_" + label].view(np.float32)), (label, kernel)
 
@@ -143,6 +148,24 @@ def test_nonfinite_and_denormal_rows_follow_the_policy(dtype, spec, ospec):
     sn = s.cpu().numpy()
     assert np.isinf(sn[1]) and np.isinf(sn[2]) and np.isnan(sn[3]) and np.isnan(sn[4])
     assert not q[1:5].any()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("spec,ospec", SPECS)
+@pytest.mark.parametrize("shape", [(2, 8), (300, 768), (700, 4096), (333, 11008), (160, 28672), (1500, 64), (40, 57344)])
+def test_staged_quantizer_bit_exact(dtype, spec, ospec, shape):
+    """The persistent shared-memory staged kernel (one CTA per SM, bulk-copy ring, refilled slots) forced on for every
+    shape it accepts: few rows per CTA, many rows per CTA (slot reuse), rows as large as half the shared memory."""
+    x = make_x(*shape, dtype, seed=9)
+    pq.lib().pq_debug_set_quant_staged(1)
+    try:
+        check(x, spec, ospec)
+        amax = F.row_absmax(x.cuda())
+        q, s = F.quantize_act_with_amax(x.cuda(), amax * 2, spec=spec)        # external row maximum
+        qo, so = O.quantize_rowwise(x, ospec, amax=(amax * 2).cpu().numpy())
+        assert np.array_equal(q.cpu().numpy(), qo) and np.array_equal(s.cpu().numpy(), so)
+    finally:
+        pq.lib().pq_debug_set_quant_staged(0)
 
 
 def test_kat_round_half_even():
