@@ -987,24 +987,49 @@ def sharded_leg(pq, torch, dist, dev, rank, world):
         rps = pq.RowParallelDynamicQuantLinear(wq_d, sw_d, None, fused=None, input_is_sharded=True, gather_output=False)
         x = torch.randn(2048, Kd, device=dev, generator=g).to(torch.bfloat16)
         down = {"layer": [Kd, Nd], "M": 2048}
-        for label, mod, xin in (("replicated", full_d, x), ("row_parallel_fused", rp, x),
-                                ("row_parallel_fused_sharded_in_scattered_out", rps, x[:, rps.k_lo:rps.k_hi].contiguous())):
+
+        def graph_ms(fn):
+            """CUDA-graph replay of TWO forwards (one per half of the modules' double buffers): ms per forward, max over ranks."""
             for _ in range(3):
-                mod(xin)
+                fn()
             torch.cuda.synchronize()
             dist.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(20):
-                y = mod(xin)
-            b.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
+            run, mode = capture(torch, dev, lambda: (fn(), fn()))
+            per = timed(torch, run, 10) / 20 if mode == "cuda_graph_replay" else timed(torch, fn, 20) / 20
+            t = torch.tensor([per], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            down[label] = {"ms": t.item(), "tops": 2 * 2048 * Nd * Kd / (t.item() * 1e-3) / 1e12}
+            return t.item(), mode
+
+        for label, mod, xin in (("replicated", full_d, x), ("row_parallel_fused", rp, x),
+                                ("row_parallel_fused_sharded_in_scattered_out", rps, x[:, rps.k_lo:rps.k_hi].contiguous())):
+            ms, mode = graph_ms(lambda: mod(xin))
+            down[label] = {"ms": ms, "tops": 2 * 2048 * Nd * Kd / (ms * 1e-3) / 1e12, "launch": mode}
         down["bit_identical"] = bool(torch.equal(rp(x), full_d(x)))
         down["fused_path_active"] = bool(rp.fused)
+        down["note"] = ("one C call per forward (pq_rowparallel_forward): row-max -> quantise -> int32 GEMM scattering into the owners' "
+                        "inboxes over NVLink -> signal-pad barrier -> reduce + dequant (+ all-gather store + barrier); no NCCL")
         res["down_proj_row_parallel"] = down
+        # the whole Llama-70B gated MLP, Megatron layout (gate/up column-parallel, no gather; down row-parallel)
+        F = pq.functional
+        mk = lambda k, n: pq.DynamicQuantLinear(k, n, bias=False, device=dev)
+        gate, up = mk(K, N), mk(K, N)
+        for mm in (gate, up):
+            mm.qweight_storage[:, :K].copy_(torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev, generator=g))
+            mm.weight_scale.copy_(torch.rand(N, device=dev, generator=g) * 1e-3)
+        mlp = pq.ParallelGatedMLP(gate, up, full_d)
+        xm = torch.randn(2048, K, device=dev, generator=g).to(torch.bfloat16)
+        one_gpu = lambda: full_d(F.act_mul(gate(xm), up(xm), "silu"))
+        want = one_gpu()
+        ms1, mode1 = graph_ms(one_gpu)
+        msp, modep = graph_ms(lambda: mlp(xm))
+        flops = 2 * 2048 * (2 * N * K + Nd * Kd)
+        res["gated_mlp_8192_28672"] = {
+            "M": 2048, "one_gpu_chain": {"ms": ms1, "tops": flops / (ms1 * 1e-3) / 1e12, "launch": mode1},
+            "tensor_parallel": {"ms": msp, "tops": flops / (msp * 1e-3) / 1e12, "launch": modep},
+            "bit_identical": bool(torch.equal(mlp(xm), want)), "fused_path_active": bool(mlp.down.fused),
+            "note": "two C calls per forward: pq_qlinear (act-quant + fused gate/up GEMM on the local column slice) and "
+                    "pq_rowparallel_forward with the gated input (silu(gate)*up max-exchanged and quantised on the fly)"}
+        del gate, up, mlp
     return res
 
 

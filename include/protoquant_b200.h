@@ -219,6 +219,44 @@ int pq_linear_create(pq_linear** out, const void* W_host, int w_dtype,
 int pq_linear_forward_host(pq_linear* h, const void* x_host, void* y_host, int64_t M);
 void pq_linear_destroy(pq_linear* h);
 
+/* SURVEY §8f-3 — the row-parallel (K-split) linear as ONE call, no NCCL on the data path.
+ * A group of 2..8 ranks (one process per GPU) shares symmetric memory: every pointer array below holds, for each
+ * rank r, the peer-mapped device address of rank r's buffer (NVLink P2P; e.g. torch symmetric memory `buffer_ptrs`). */
+typedef struct pq_symm_group {
+  int32_t rank, world;
+  void* inbox[8];     /* int32 [world][cap][per_n]: slot s receives rank s's partial sums of this rank's columns */
+  void* out[8];       /* y_dtype [cap][ldy]: the gathered output (only read when gather_output != 0)          */
+  float* amax[8];     /* fp32 [world][cap]: row-maximum exchange (only read when the input is K-sharded)       */
+  uint32_t* pads[8];  /* >= 32 uint32, zero-initialised once: cross-rank signal pads of pq_symm_barrier        */
+  int64_t cap;        /* row capacity of inbox / out / amax                                                    */
+} pq_symm_group;
+
+/* Cross-rank barrier on `stream` through the signal pads (channel 0..3): returns once every rank's kernel has
+ * arrived; peer stores issued by earlier kernels of any rank are visible to later kernels of every rank.
+ * Self-resetting (CUDA-graph replay safe), bounded spins (a missing rank traps after 4 s instead of hanging). */
+int pq_symm_barrier(const pq_symm_group* sg, int channel, void* stream);
+
+/* y = linear(x) for a weight split along K over the group: this rank holds Wq [N, K_slice] (its K-slice of every
+ * output channel), the full s_w [N] / bias [N].
+ *   x  [M, K_in] x_dtype row stride ldx.  input_is_sharded == 0: x is the replicated activation, this rank uses
+ *      columns [k_lo, k_lo + K_slice) and the row maximum is taken over all K_in columns locally.
+ *      input_is_sharded != 0: x is this rank's K-slice (K_in == K_slice); the row maxima are exchanged through
+ *      sg->amax.  up != NULL (K-sharded only): the input is act(x) * up (enum pq_act; x = gate), [M, K_slice] each.
+ *   Launches: row-max (+ barrier) + quantise + int32 GEMM scattering into the owners' inboxes + barrier +
+ *   reduce/dequant of this rank's per_n output columns (stored into every rank's sg->out at column rank * per_n when
+ *   gather_output, followed by a barrier; else into y_local [M, n_mine] row stride ldy).
+ *   per_n: output columns per rank (multiple of 8, per_n * world >= N); ldy: row stride of sg->out / y_local.
+ *   xq_ws [M, ld16(K_slice)] int8, sx_ws [M] fp32, amax_ws [M] fp32 (replicated input only): caller-owned scratch.
+ * Bit-identical to the unsplit pq_qlinear for any world size: the K-shards quantise with the global row maximum
+ * and the reduction runs on the exact int32 partial sums before ONE dequant epilogue. */
+int pq_rowparallel_forward(const void* x, const void* up, int x_dtype, int act, int64_t ldx, int64_t ldu,
+                           int input_is_sharded, int64_t K_in, int64_t k_lo,
+                           const int8_t* Wq, int64_t ldb, const float* s_w, const float* bias,
+                           const pq_symm_group* sg, int gather_output, void* y_local, int y_dtype, int64_t ldy,
+                           int8_t* xq_ws, float* sx_ws, float* amax_ws,
+                           int64_t M, int64_t N, int64_t K_slice, int64_t per_n,
+                           const pq_quant_spec* spec, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,11 +26,19 @@ EXPORTS = (
     "pq_linear_create", "pq_linear_forward_host", "pq_linear_destroy",
     "pq_norm_quant", "pq_act_mul_quant",
     "pq_row_absmax", "pq_act_quant_amax", "pq_qgemm_i32_scatter", "pq_reduce_dequant",
+    "pq_symm_barrier", "pq_rowparallel_forward",
 )
 
 
 class PQQuantSpec(ctypes.Structure):
     _fields_ = [("scale_mode", ctypes.c_int32), ("eps", ctypes.c_float), ("qmin", ctypes.c_int32)]
+
+
+class PQSymmGroup(ctypes.Structure):
+    """pq_symm_group: per-rank peer-mapped addresses of the symmetric buffers of a row-parallel layer."""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32),
+                ("inbox", ctypes.c_void_p * 8), ("out", ctypes.c_void_p * 8), ("amax", ctypes.c_void_p * 8),
+                ("pads", ctypes.c_void_p * 8), ("cap", ctypes.c_int64)]
 
 
 class ProtoquantError(RuntimeError):
@@ -85,6 +93,12 @@ def _declare(lib):
     lib.pq_reduce_dequant.argtypes = [c.POINTER(vp), i32, i64, vp, vp, vp, c.POINTER(vp), i32, i32, i64, i64, i64, vp]
     lib.pq_act_mul_quant.restype = i32
     lib.pq_act_mul_quant.argtypes = [vp, vp, i32, i32, i64, i64, i64, i64, vp, i64, vp, vp, i64, specp, vp]
+    sgp = c.POINTER(PQSymmGroup)
+    lib.pq_symm_barrier.restype = i32
+    lib.pq_symm_barrier.argtypes = [sgp, i32, vp]
+    lib.pq_rowparallel_forward.restype = i32
+    lib.pq_rowparallel_forward.argtypes = [vp, vp, i32, i32, i64, i64, i32, i64, i64, vp, i64, vp, vp, sgp, i32, vp, i32, i64,
+                                           vp, vp, vp, i64, i64, i64, i64, specp, vp]
     if hasattr(lib, "pq_debug_set_quant_config"):
         lib.pq_debug_set_quant_config.restype = None
         lib.pq_debug_set_quant_config.argtypes = [i32, i32]

@@ -71,7 +71,24 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
                          int8_t* xq, int64_t ldq, float* s, int transpose,
                          const pq_quant_spec& spec, cudaStream_t stream,
                          const void* prefetch = nullptr, long long prefetch_bytes = 0,
-                         const float* amax_in = nullptr);
+                         const float* amax_in = nullptr, int amax_slots = 1, long long amax_stride = 0);
+
+// amax[m] = max_k |x[m,k]| stored to every dsts[d][m] (rowparallel.cu)
+int launch_row_absmax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, float* const* dsts, int n_dst,
+                      cudaStream_t st);
+// y = cast(((float(sum of the int32 parts) * s_x[m]) * s_w[n]) + bias[n]) written to every ys[d] (rowparallel.cu)
+int launch_reduce_dequant(const int32_t* const* parts, int n_parts, int64_t ld_part,
+                          const float* s_x, const float* s_w, const float* bias,
+                          void* const* ys, int n_ys, int y_dtype, int64_t ldy, int64_t M, int64_t N, cudaStream_t st);
+
+// act(gate) [* up] -> int8 (+ scale), or -- n_amax_out > 0 -- only the row maxima of that product into amax_out[d][row];
+// amax_in: quantise with the maximum over `amax_slots` external arrays (fused_quant.cu)
+int launch_act_mul_quant(const void* gate, const void* up, int dtype, int act,
+                         int64_t M, int64_t K, int64_t ldg, int64_t ldu,
+                         int8_t* hq, int64_t ldq, float* s_h, void* h, int64_t ldh,
+                         const pq_quant_spec& spec, cudaStream_t stream,
+                         const float* amax_in, int amax_slots, long long amax_stride,
+                         float* const* amax_out, int n_amax_out);
 
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,

@@ -293,6 +293,12 @@ struct ActArgs {
   int8_t* hq; float* s_out; void* h;
   long long M, ldg, ldu, ldq, ldh;
   int nvec; int act; int scale_mode; float qeps;
+  // row-parallel consumer: the row maximum of h spans every rank's column slice.
+  //   n_amax_out > 0: "statistics" launch -- only the local row maxima are computed and stored to amax_out[d][row]
+  //                   (this rank's slot in every rank's exchange buffer); no codes, no scales;
+  //   amax_in != 0:   quantise with the maximum over `amax_slots` arrays (stride `amax_stride`) instead of the local one.
+  const float* amax_in; int amax_slots; long long amax_stride;
+  float* amax_out[8]; int n_amax_out;
 };
 
 // SiLU uses ex2.approx + rcp.approx (two MUFU ops, ~2^-21 relative error: below half an ulp of every storage
@@ -375,6 +381,12 @@ act_mul_quant_kernel(const ActArgs a) {
   else body(std::integral_constant<int, PQ_ACT_IDENTITY>{});
   float amax = regs_absmax<T, VPT>(v);
   amax = row_reduce<TPR, ROWS, true>(amax, red, row_in_cta, t);
+  if (a.n_amax_out > 0) {
+    if (row_ok && t == 0)
+      for (int d = 0; d < a.n_amax_out; ++d) a.amax_out[d][row] = amax;
+    return;
+  }
+  if (a.amax_in != nullptr && row_ok) amax = given_amax(a.amax_in, a.amax_slots, a.amax_stride, row);
   const RowQ rq = make_rowq(amax, a.scale_mode, a.qeps);
   if (row_ok && t == 0) a.s_out[row] = rq.s;
   if (!row_ok) return;
@@ -504,15 +516,27 @@ extern "C" int pq_act_mul_quant(const void* gate, const void* up, int dtype, int
                                 int64_t M, int64_t K, int64_t ldg, int64_t ldu,
                                 int8_t* hq, int64_t ldq, float* s_h, void* h, int64_t ldh,
                                 const pq_quant_spec* spec_in, void* stream) {
+  return pq::launch_act_mul_quant(gate, up, dtype, act, M, K, ldg, ldu, hq, ldq, s_h, h, ldh, resolve_spec(spec_in),
+                                  (cudaStream_t)stream, nullptr, 0, 0, nullptr, 0);
+}
+
+int pq::launch_act_mul_quant(const void* gate, const void* up, int dtype, int act,
+                             int64_t M, int64_t K, int64_t ldg, int64_t ldu,
+                             int8_t* hq, int64_t ldq, float* s_h, void* h, int64_t ldh,
+                             const pq_quant_spec& spec, cudaStream_t stream,
+                             const float* amax_in, int amax_slots, long long amax_stride,
+                             float* const* amax_out, int n_amax_out) {
   int rc = check_device(nullptr);
   if (rc) return rc;
-  const pq_quant_spec spec = resolve_spec(spec_in);
   rc = check_spec(spec, "pq_act_mul_quant");
   if (rc) return rc;
   if (M < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: bad shape M=%lld K=%lld", (long long)M, (long long)K);
   if (act < PQ_ACT_IDENTITY || act > PQ_ACT_GELU_TANH) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: unknown activation %d", act);
   if (M == 0) return PQ_OK;
-  if (!gate || !hq || !s_h) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: null pointer");
+  const bool stats_only = n_amax_out > 0;
+  if (n_amax_out < 0 || n_amax_out > 8 || (stats_only && !amax_out)) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: bad amax destination list");
+  if (!gate || (!stats_only && (!hq || !s_h))) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: null pointer");
+  if (stats_only) { hq = nullptr; ldq = K; h = nullptr; }
   if (ldg < K || (up && ldu < K) || ldq < K || (h && ldh < K)) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: leading dimension smaller than K");
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "pq_act_mul_quant: M too large");
   const int esz = dtype_size(dtype);
@@ -527,7 +551,10 @@ extern "C" int pq_act_mul_quant(const void* gate, const void* up, int dtype, int
   a.gate = gate; a.up = up; a.hq = hq; a.s_out = s_h; a.h = h;
   a.M = M; a.ldg = ldg; a.ldu = ldu; a.ldq = ldq; a.ldh = ldh;
   a.nvec = (int)(K / epv); a.act = act; a.scale_mode = mode_bits(spec); a.qeps = spec.eps;
-  cudaStream_t st = (cudaStream_t)stream;
+  a.amax_in = amax_in; a.amax_slots = amax_slots; a.amax_stride = amax_stride;
+  a.n_amax_out = n_amax_out;
+  for (int d = 0; d < 8; ++d) a.amax_out[d] = d < n_amax_out ? amax_out[d] : nullptr;
+  cudaStream_t st = stream;
   switch (dtype) {
     case PQ_F32: return dispatch_cfg<float, ActLauncher>(a, M, a.nvec, st);
     case PQ_F16: return dispatch_cfg<__half, ActLauncher>(a, M, a.nvec, st);

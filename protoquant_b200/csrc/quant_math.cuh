@@ -80,6 +80,15 @@ template <> __device__ __forceinline__ float u16_mag_to_float<__half>(uint32_t p
 }
 template <> __device__ __forceinline__ float u16_mag_to_float<float>(uint32_t) { return 0.f; }
 
+// Row maximum supplied from outside (row-parallel shards): the maximum over `slots` arrays of M
+// floats `stride` elements apart -- one per K-shard, written by the peers into this rank's symmetric memory -- read
+// through L2 (ld.cg: the producers are other GPUs).  NaN propagates (integer max on the magnitude bits).
+__device__ __forceinline__ float given_amax(const float* amax_in, int slots, long long stride, int64_t row) {
+  float a = __ldcg(amax_in + row);
+  for (int sl = 1; sl < slots; ++sl) a = mag_max(a, __ldcg(amax_in + sl * stride + row));
+  return a;
+}
+
 // ---- per-row quantisation parameters --------------------------------------------
 // Policy for rows the "fast" arithmetic cannot take (include/protoquant_b200.h "Non-finite and denormal input"):
 //   * amax propagates NaN and inf (see above), s = amax/127 in IEEE arithmetic: NaN -> NaN, inf -> inf;

@@ -17,10 +17,12 @@ namespace {
 
 using namespace qmath;
 
+struct AmaxDst { float* p[8]; int n; };   // the row maxima are stored to every p[d][row] (exchange slots of the peers)
+
 // one CTA per row, 16-byte loads when VEC
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
-row_absmax_kernel(const T* __restrict__ x, int64_t K, int64_t ldx, float* __restrict__ amax_out) {
+row_absmax_kernel(const T* __restrict__ x, int64_t K, int64_t ldx, const AmaxDst dst) {
   constexpr int EPV = VecTraits<T>::EPV;
   __shared__ float red[8];
   ptx::griddep_launch_dependents();
@@ -46,16 +48,16 @@ row_absmax_kernel(const T* __restrict__ x, int64_t K, int64_t ldx, float* __rest
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int w = 1; w < 8; ++w) amax = mag_max(amax, red[w]);
-    amax_out[blockIdx.x] = amax;
+    for (int d = 0; d < dst.n; ++d) dst.p[d][blockIdx.x] = amax;
   }
 }
 
 template <typename T>
-int launch_absmax(const void* x, int64_t M, int64_t K, int64_t ldx, float* amax, cudaStream_t st) {
+int launch_absmax(const void* x, int64_t M, int64_t K, int64_t ldx, const AmaxDst& dst, cudaStream_t st) {
   constexpr int EPV = VecTraits<T>::EPV;
   const bool vec = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) && ((ldx * (int64_t)sizeof(T)) % 16 == 0);
-  if (vec) row_absmax_kernel<T, true><<<(unsigned)M, 256, 0, st>>>((const T*)x, K, ldx, amax);
-  else row_absmax_kernel<T, false><<<(unsigned)M, 256, 0, st>>>((const T*)x, K, ldx, amax);
+  if (vec) row_absmax_kernel<T, true><<<(unsigned)M, 256, 0, st>>>((const T*)x, K, ldx, dst);
+  else row_absmax_kernel<T, false><<<(unsigned)M, 256, 0, st>>>((const T*)x, K, ldx, dst);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   PQ_CUDA(cudaGetLastError());
   return PQ_OK;
@@ -151,20 +153,32 @@ int launch_reduce(const ReduceArgs& a, cudaStream_t st) {
 
 using namespace pq;
 
-extern "C" int pq_row_absmax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, float* amax, void* stream) {
+int pq::launch_row_absmax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, float* const* dsts, int n_dst,
+                          cudaStream_t st) {
   int rc = check_device(nullptr);
   if (rc) return rc;
   if (M < 0 || K < 1 || ldx < K) PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: bad shape M=%lld K=%lld ldx=%lld", (long long)M, (long long)K, (long long)ldx);
   if (M == 0) return PQ_OK;
-  if (!x || !amax) PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: null pointer");
+  if (!x || !dsts || n_dst < 1 || n_dst > 8) PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: null pointer or bad destination count");
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: M too large");
-  cudaStream_t st = (cudaStream_t)stream;
+  AmaxDst dst = {};
+  dst.n = n_dst;
+  for (int d = 0; d < n_dst; ++d) {
+    if (!dsts[d]) PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: null destination %d", d);
+    dst.p[d] = dsts[d];
+  }
   switch (x_dtype) {
-    case PQ_F32: return launch_absmax<float>(x, M, K, ldx, amax, st);
-    case PQ_F16: return launch_absmax<__half>(x, M, K, ldx, amax, st);
-    case PQ_BF16: return launch_absmax<__nv_bfloat16>(x, M, K, ldx, amax, st);
+    case PQ_F32: return launch_absmax<float>(x, M, K, ldx, dst, st);
+    case PQ_F16: return launch_absmax<__half>(x, M, K, ldx, dst, st);
+    case PQ_BF16: return launch_absmax<__nv_bfloat16>(x, M, K, ldx, dst, st);
     default: PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: unsupported dtype %d", x_dtype);
   }
+}
+
+extern "C" int pq_row_absmax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, float* amax, void* stream) {
+  float* one[1] = {amax};
+  if (!amax && M > 0) PQ_FAIL(PQ_ERR_ARG, "pq_row_absmax: null pointer");
+  return launch_row_absmax(x, x_dtype, M, K, ldx, one, 1, (cudaStream_t)stream);
 }
 
 extern "C" int pq_act_quant_amax(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, const float* amax,
@@ -188,6 +202,13 @@ extern "C" int pq_reduce_dequant(const int32_t* const* parts, int n_parts, int64
                                  const float* s_x, const float* s_w, const float* bias,
                                  void* const* ys, int n_ys, int y_dtype, int64_t ldy,
                                  int64_t M, int64_t N, void* stream) {
+  return launch_reduce_dequant(parts, n_parts, ld_part, s_x, s_w, bias, ys, n_ys, y_dtype, ldy, M, N, (cudaStream_t)stream);
+}
+
+int pq::launch_reduce_dequant(const int32_t* const* parts, int n_parts, int64_t ld_part,
+                              const float* s_x, const float* s_w, const float* bias,
+                              void* const* ys, int n_ys, int y_dtype, int64_t ldy,
+                              int64_t M, int64_t N, cudaStream_t st) {
   int rc = check_device(nullptr);
   if (rc) return rc;
   if (M < 0 || N < 0) PQ_FAIL(PQ_ERR_ARG, "pq_reduce_dequant: bad shape");
@@ -211,7 +232,6 @@ extern "C" int pq_reduce_dequant(const int32_t* const* parts, int n_parts, int64
   }
   a.s_x = s_x; a.s_w = s_w; a.bias = bias;
   a.ld_part = ld_part; a.ldy = ldy; a.M = M; a.N = N; a.n_parts = n_parts; a.n_ys = n_ys;
-  cudaStream_t st = (cudaStream_t)stream;
   switch (y_dtype) {
     case PQ_F32: return launch_reduce<float>(a, st);
     case PQ_F16: return launch_reduce<__half>(a, st);

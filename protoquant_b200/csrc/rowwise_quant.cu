@@ -57,7 +57,7 @@ __global__ void __launch_bounds__((TPR > 256 ? TPR : 256))
 rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t ldx,
                          int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
                          int scale_mode, float eps, const uint8_t* __restrict__ pf, long long pf_bytes,
-                         const float* __restrict__ amax_in) {
+                         const float* __restrict__ amax_in, int amax_slots, long long amax_stride) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
@@ -114,7 +114,7 @@ rowwise_quant_vec_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t l
     for (int w = 0; w < WPR; ++w) amax = mag_max(amax, red[row_in_cta][w]);
   }
   // row-parallel shards quantise a K-slice with the |.|-max of the WHOLE row (pq_act_quant_amax)
-  if (amax_in != nullptr && row_ok) amax = __ldg(amax_in + row);
+  if (amax_in != nullptr && row_ok) amax = given_amax(amax_in, amax_slots, amax_stride, row);
 
   const RowQ rq = make_rowq(amax, scale_mode, eps);
   if (row_ok && t == 0) s_out[row] = rq.s;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(STG_THREADS, 1)
 rowwise_quant_staged_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_t ldx,
                             int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
                             int scale_mode, float eps, const uint8_t* __restrict__ pf, long long pf_bytes,
-                            const float* __restrict__ amax_in, int slots) {
+                            const float* __restrict__ amax_in, int amax_slots, long long amax_stride, int slots) {
   constexpr int EPV = VecTraits<T>::EPV;
   extern __shared__ __align__(128) uint8_t stg_smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg_smem);                       // [slots]
@@ -227,7 +227,7 @@ rowwise_quant_staged_kernel(const T* __restrict__ x, int64_t M, int nvec, int64_
     if ((t & 31) == 0) rr[t >> 5] = amax;
     ptx::named_bar_sync(1 + g, STG_TPR);
     amax = mag_max(mag_max(rr[0], rr[1]), mag_max(rr[2], rr[3]));
-    if (amax_in != nullptr) amax = __ldg(amax_in + row);
+    if (amax_in != nullptr) amax = given_amax(amax_in, amax_slots, amax_stride, row);
     const RowQ rq = make_rowq(amax, scale_mode, eps);
     if (t == 0) s_out[row] = rq.s;
     // pass 2: quantise from shared memory
@@ -277,7 +277,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int64_t ldx,
                              int8_t* __restrict__ xq, int64_t ldq, float* __restrict__ s_out,
-                             int transpose, int scale_mode, float eps, const float* __restrict__ amax_in) {
+                             int transpose, int scale_mode, float eps, const float* __restrict__ amax_in,
+                             int amax_slots, long long amax_stride) {
   __shared__ float red[8];
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
@@ -291,7 +292,7 @@ rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int6
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < 8; ++w) amax = mag_max(amax, red[w]);
-  if (amax_in != nullptr) amax = __ldg(amax_in + row);
+  if (amax_in != nullptr) amax = given_amax(amax_in, amax_slots, amax_stride, row);
   const RowQ rq = make_rowq(amax, scale_mode, eps);
   if (threadIdx.x == 0) s_out[row] = rq.s;
   for (int64_t k = threadIdx.x; k < K; k += 256) {
@@ -407,13 +408,13 @@ rowwise_quant_transposed_kernel(const T* __restrict__ x, int64_t M, int64_t K, i
 template <typename T, int TPR, int VPT>
 int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int64_t ldq,
                float* s, const pq_quant_spec& spec, cudaStream_t st, const void* pf, long long pf_bytes,
-               const float* amax_in) {
+               const float* amax_in, int amax_slots, long long amax_stride) {
   constexpr int THREADS = (TPR > 256 ? TPR : 256);
   constexpr int ROWS = THREADS / TPR;
   const int64_t grid = (M + ROWS - 1) / ROWS;
   PQ_CUDA(launch_pdl(rowwise_quant_vec_kernel<T, TPR, VPT>, (unsigned)grid, THREADS, st,
                      (const T*)x, M, nvec, ldx, xq, ldq, s, mode_bits(spec), spec.eps,
-                     (const uint8_t*)pf, pf_bytes, amax_in));
+                     (const uint8_t*)pf, pf_bytes, amax_in, amax_slots, amax_stride));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;
 }
@@ -421,7 +422,7 @@ int launch_vec(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int6
 template <typename T>
 int launch_staged(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, int64_t ldq, float* s,
                   const pq_quant_spec& spec, cudaStream_t st, const void* pf, long long pf_bytes,
-                  const float* amax_in, int num_sms, int slots) {
+                  const float* amax_in, int amax_slots, long long amax_stride, int num_sms, int slots) {
   const int dyn = STG_HEADER + slots * nvec * 16;
   static gemm::PerDeviceOnce once;
   const cudaError_t e = once.run([&](int*) {
@@ -440,7 +441,7 @@ int launch_staged(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, i
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 1 : 0;
   PQ_CUDA(cudaLaunchKernelEx(&cfg, rowwise_quant_staged_kernel<T>, (const T*)x, M, nvec, ldx, xq, ldq, s,
-                             mode_bits(spec), spec.eps, (const uint8_t*)pf, pf_bytes, amax_in, slots));
+                             mode_bits(spec), spec.eps, (const uint8_t*)pf, pf_bytes, amax_in, amax_slots, amax_stride, slots));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return PQ_OK;
 }
@@ -448,7 +449,7 @@ int launch_staged(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, i
 template <typename T>
 int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq,
              float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st,
-             const void* pf, long long pf_bytes, const float* amax_in) {
+             const void* pf, long long pf_bytes, const float* amax_in, int amax_slots, long long amax_stride) {
   constexpr int EPV = VecTraits<T>::EPV;
   if (M == 0) return PQ_OK;
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
@@ -472,7 +473,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
                       (K / EPV <= 8192);
   if (!vec_ok) {
     PQ_CUDA(launch_pdl(rowwise_quant_generic_kernel<T>, (unsigned)M, 256u, st,
-                       (const T*)x, M, K, ldx, xq, ldq, s, 0, mode_bits(spec), spec.eps, amax_in));
+                       (const T*)x, M, K, ldx, xq, ldq, s, 0, mode_bits(spec), spec.eps, amax_in, amax_slots, amax_stride));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return PQ_OK;
   }
@@ -498,7 +499,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
       const bool auto_ok = row_bytes >= 8192 && M >= num_sms &&
                            ((row_bytes >= 16384 && bytes <= (64LL << 20)) || M <= 1024);
       if (slots >= 2 && (staged > 0 || auto_ok))
-        return launch_staged<T>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes, amax_in, num_sms, (int)slots);
+        return launch_staged<T>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes, amax_in, amax_slots, amax_stride, num_sms, (int)slots);
     }
   }
   // Pick (threads per row, vectors per thread): cover the row with as few idle lanes as possible,
@@ -522,7 +523,7 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
     if (score < best_score) { best_score = score; best_tpr = tpr; best_vpt = vpt; }
   }
   if (g_force_tpr > 0 && g_force_vpt > 0 && g_force_tpr * g_force_vpt >= nvec) { best_tpr = g_force_tpr; best_vpt = g_force_vpt; }
-#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes, amax_in);
+#define PQ_CASE_V(TPR, VPT) if (best_tpr == TPR && best_vpt == VPT) return launch_vec<T, TPR, VPT>(x, M, nvec, ldx, xq, ldq, s, spec, st, pf, pf_bytes, amax_in, amax_slots, amax_stride);
 #define PQ_CASE_T(TPR) PQ_CASE_V(TPR, 2) PQ_CASE_V(TPR, 3) PQ_CASE_V(TPR, 4) PQ_CASE_V(TPR, 6) PQ_CASE_V(TPR, 8)
   PQ_CASE_T(32) PQ_CASE_T(64) PQ_CASE_T(128) PQ_CASE_T(256) PQ_CASE_T(512) PQ_CASE_T(1024)
 #undef PQ_CASE_T
@@ -535,7 +536,8 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
 int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
                          int8_t* xq, int64_t ldq, float* s, int transpose,
                          const pq_quant_spec& spec, cudaStream_t stream,
-                         const void* prefetch, long long prefetch_bytes, const float* amax_in) {
+                         const void* prefetch, long long prefetch_bytes, const float* amax_in,
+                         int amax_slots, long long amax_stride) {
   if (((uintptr_t)prefetch & 15) || prefetch_bytes < 16 || !g_weight_prefetch) { prefetch = nullptr; prefetch_bytes = 0; }
   if (M < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: bad shape M=%lld K=%lld", (long long)M, (long long)K);
   if (M > 0 && (!x || !xq || !s)) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: null pointer");
@@ -547,9 +549,9 @@ int launch_rowwise_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64
   if (spec.qmin != -128 && spec.qmin != -127)
     PQ_FAIL(PQ_ERR_ARG, "rowwise quant: qmin must be -128 or -127");
   switch (x_dtype) {
-    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in);
-    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in);
-    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in);
+    case PQ_F32: return dispatch<float>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in, amax_slots, amax_stride);
+    case PQ_F16: return dispatch<__half>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in, amax_slots, amax_stride);
+    case PQ_BF16: return dispatch<__nv_bfloat16>(x, M, K, ldx, xq, ldq, s, transpose, spec, stream, prefetch, prefetch_bytes, amax_in, amax_slots, amax_stride);
     default: PQ_FAIL(PQ_ERR_ARG, "rowwise quant: unsupported dtype %d", x_dtype);
   }
 }

@@ -243,11 +243,12 @@ class RowParallelDynamicQuantLinear(nn.Module):
       the unsharded quantizer.
     * The K-slices' int32 partial sums are exact and associative, so the reduce step is done on int32 and the
       dequant epilogue runs once on the sum: the output is bit-identical to the 1-GPU module for any world size.
-    * Fused exchange (CUDA + symmetric memory): the GEMM epilogue stores each output-column block straight into
-      the inbox of the rank that owns it (NVLink peer stores, `pq_qgemm_i32_scatter`); after one barrier the
+    * Fused exchange (CUDA + symmetric memory), ONE C call per forward (`pq_rowparallel_forward`): the row maxima
+      of a K-sharded input are exchanged through symmetric memory, the GEMM epilogue stores each output-column
+      block straight into the inbox of the rank that owns it (NVLink peer stores); after a signal-pad barrier the
       owner sums its `world` inboxes, applies scales and bias and -- with `gather_output` -- writes the finished
-      slice into every rank's output buffer (`pq_reduce_dequant`): GEMM + reduce-scatter + all-gather in two
-      kernels and two barriers, no NCCL call on the data path.
+      slice into every rank's output buffer: GEMM + reduce-scatter + all-gather as a fixed sequence of launches
+      with in-stream cross-rank barriers, no NCCL call and no host synchronisation, CUDA-graph capturable.
     * Fallback (gloo, or no symmetric memory): int32 all-reduce(SUM) of the partial sums + local epilogue.
     """
 
@@ -276,6 +277,7 @@ class RowParallelDynamicQuantLinear(nn.Module):
         self.fused = fused
         self.fused_error = None
         self._symm = None
+        self._ws = None
         self._flip = 0
         self.k_lo, self.k_hi = shard_bounds(self.in_features, self.world, self.rank, align=16)
         if self.k_hi <= self.k_lo:
@@ -305,21 +307,37 @@ class RowParallelDynamicQuantLinear(nn.Module):
         return self.ops.quantize_with_amax(xs, amax, self.spec)
 
     def _symm_buffers(self, rows: int, dtype, device):
+        """Two sets (double buffering) of symmetric buffers + one signal pad, and the pq_symm_group structs the C
+        entry point takes: every rank's peer-mapped addresses of inbox / out / amax / pads."""
+        import ctypes
         import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
         key = (dtype,)
         if self._symm is not None and self._symm[0] == key and self._symm[1] >= rows:
             return self._symm[1], self._symm[2]
         cap = max(rows, 16)
         group = self.group if self.group is not None else dist.group.WORLD
-        bufs = []
+        pads = symm_mem.empty((64,), dtype=torch.int32, device=device)
+        pads.zero_()
+        hp = symm_mem.rendezvous(pads, group)
+        sets = []
         for _ in range(2):
             inbox = symm_mem.empty((self.world, cap, self.per_n), dtype=torch.int32, device=device)
             hi = symm_mem.rendezvous(inbox, group)
             out = symm_mem.empty((cap, self.world * self.per_n), dtype=dtype, device=device)
             ho = symm_mem.rendezvous(out, group)
-            bufs.append((inbox, hi, out, ho))
-        self._symm = (key, cap, bufs)
-        return cap, bufs
+            amax = symm_mem.empty((self.world, cap), dtype=torch.float32, device=device)
+            ha = symm_mem.rendezvous(amax, group)
+            sg = _lib.PQSymmGroup()
+            sg.rank, sg.world, sg.cap = self.rank, self.world, cap
+            for r in range(self.world):
+                sg.inbox[r], sg.out[r], sg.amax[r], sg.pads[r] = (int(hi.buffer_ptrs[r]), int(ho.buffer_ptrs[r]),
+                                                                  int(ha.buffer_ptrs[r]), int(hp.buffer_ptrs[r]))
+            sets.append({"inbox": inbox, "out": out, "amax": amax, "handles": (hi, ho, ha), "sg": sg, "sgp": ctypes.byref(sg)})
+        torch.cuda.synchronize(device)
+        dist.barrier(group)            # every rank's pad is zero before anybody signals
+        self._symm = (key, cap, sets, (pads, hp))
+        return cap, sets
 
     def _enable_fused(self, rows: int, dtype, device) -> bool:
         """Symmetric-memory setup: the only step that may fail softly; all ranks agree on the outcome."""
@@ -342,43 +360,78 @@ class RowParallelDynamicQuantLinear(nn.Module):
         self.fused = False
         return False
 
-    def _forward_fused(self, xq, s_x, M: int, out_dtype) -> torch.Tensor:
-        cap, bufs = self._symm[1], self._symm[2]
-        inbox, hi, out, ho = bufs[self._flip]
-        self._flip ^= 1
-        slot = cap * self.per_n * 4                      # bytes of one source rank's inbox
-        F.qgemm_i32_scatter(xq, self.qweight, [int(p) + self.rank * slot for p in hi.buffer_ptrs],
-                            self.per_n, self.per_n)
-        hi.barrier()                                     # every rank's partial sums have landed
-        n_mine = self.n_hi - self.n_lo
-        parts = [inbox.data_ptr() + s * slot for s in range(self.world)]
-        sw = self.weight_scale[self.n_lo:self.n_hi]
-        b = self.bias[self.n_lo:self.n_hi] if self.bias is not None else None
-        if not self.gather_output:
-            y = torch.empty((M, n_mine), dtype=out_dtype, device=xq.device)
-            if n_mine:
-                F.reduce_dequant(parts, self.per_n, s_x, sw, b, [y.data_ptr()], n_mine, out_dtype, M, n_mine)
-            return y
-        esz = out.element_size()
-        if n_mine:
-            F.reduce_dequant(parts, self.per_n, s_x, sw, b, [int(p) + self.n_lo * esz for p in ho.buffer_ptrs],
-                             self.world * self.per_n, out_dtype, M, n_mine)
-        ho.barrier()
-        return out[:M, : self.out_features]
+    def _workspace(self, rows: int, device):
+        if self._ws is None or self._ws[0].shape[0] < rows or self._ws[0].device != device:
+            cap = max(rows, 16)
+            self._ws = (torch.empty((cap, self.qweight_storage.shape[1]), dtype=torch.int8, device=device),
+                        torch.empty((cap,), dtype=torch.float32, device=device),
+                        torch.empty((cap,), dtype=torch.float32, device=device))
+        return self._ws
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """With `gather_output` on the fused path the result is a VIEW into a double-buffered symmetric-memory
-        buffer, overwritten by the second forward() after this one; clone it to keep it longer."""
+    def _forward_fused(self, x2: torch.Tensor, up2: Optional[torch.Tensor], act: str, M: int, out_dtype) -> torch.Tensor:
+        """ONE C call (pq_rowparallel_forward): row maxima (exchanged through symmetric memory when the input is
+        K-sharded) -> quantise -> int32 GEMM scattering into the owners' inboxes -> barrier -> reduce + dequant
+        (+ all-gather store + barrier).  No NCCL, no host sync: a fixed launch sequence, CUDA-graph capturable."""
+        from . import _lib
+        sets = self._symm[2]
+        st = sets[self._flip]
+        self._flip ^= 1
+        xq_ws, sx_ws, amax_ws = self._workspace(M, x2.device)
+        ks = self.k_hi - self.k_lo
+        n_mine = self.n_hi - self.n_lo
+        y_local = None
+        if not self.gather_output:
+            y_local = torch.empty((M, n_mine), dtype=out_dtype, device=x2.device)
+        ldy = self.world * self.per_n if self.gather_output else max(n_mine, 1)
+        with F._on(x2, up2, self.qweight_storage, self.weight_scale, self.bias):
+            rc = _lib.lib().pq_rowparallel_forward(
+                x2.data_ptr(), up2.data_ptr() if up2 is not None else None, F._DT[x2.dtype], F._ACTS[act],
+                x2.stride(0), up2.stride(0) if up2 is not None else 0,
+                1 if self.input_is_sharded else 0, x2.shape[1], 0 if self.input_is_sharded else self.k_lo,
+                self.qweight_storage.data_ptr(), self.qweight_storage.stride(0), self.weight_scale.data_ptr(),
+                self.bias.data_ptr() if self.bias is not None else None,
+                st["sgp"], 1 if self.gather_output else 0,
+                y_local.data_ptr() if (y_local is not None and n_mine) else (xq_ws.data_ptr() if not self.gather_output else None),
+                F._DT[out_dtype], ldy, xq_ws.data_ptr(), sx_ws.data_ptr(), amax_ws.data_ptr(),
+                M, self.out_features, ks, self.per_n, F._specp(self.spec), F._stream(x2.device))
+        _lib.check(rc, "pq_rowparallel_forward")
+        if not self.gather_output:
+            return y_local
+        return st["out"][:M, : self.out_features]
+
+    def _check_fused_input(self, x2, up2):
+        want = (self.k_hi - self.k_lo) if self.input_is_sharded else self.in_features
+        if x2.shape[1] != want:
+            raise ValueError(f"expected {want} input columns, got {x2.shape[1]}")
+        for t in (x2, up2):
+            if t is not None and (t.stride(1) != 1 or t.dtype not in F._DT):
+                raise TypeError("inputs must have unit column stride and a supported dtype")
+        if up2 is not None and (up2.shape != x2.shape or up2.dtype != x2.dtype or not self.input_is_sharded):
+            raise ValueError("a gated input needs input_is_sharded=True and gate / up of equal shape and dtype")
+
+    def forward(self, x: torch.Tensor, up: Optional[torch.Tensor] = None, act: str = "silu") -> torch.Tensor:
+        """y = linear(x), or -- `up` given, K-sharded input only -- y = linear(act(x) * up) with the activation product
+        computed and quantised on the fly (the Llama MLP's down projection fed by column-parallel gate / up slices).
+        With `gather_output` on the fused path the result is a VIEW into a double-buffered symmetric-memory buffer,
+        overwritten by the second forward() after this one; clone it to keep it longer."""
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
+        up2 = up.reshape(-1, up.shape[-1]) if up is not None else None
         out_dtype = self.out_dtype or x.dtype
-        xq, s_x = self._quantize(x2)
         M = x2.shape[0]
         n_out = self.out_features if (self.gather_output or self.world == 1) else self.n_hi - self.n_lo
-        if self.world > 1 and self.ops is _CudaShardOps and x2.is_cuda and self.fused is not False:
-            if self._enable_fused(M, out_dtype, xq.device):
+        if M and self.world > 1 and self.ops is _CudaShardOps and x2.is_cuda and self.fused is not False:
+            if self._enable_fused(M, out_dtype, x2.device):
                 self.fused = True
-                return self._forward_fused(xq, s_x, M, out_dtype).reshape(*lead, n_out)
+                if x2.stride(-1) != 1:
+                    x2 = x2.contiguous()
+                if up2 is not None and up2.stride(-1) != 1:
+                    up2 = up2.contiguous()
+                self._check_fused_input(x2, up2)
+                return self._forward_fused(x2, up2, act, M, out_dtype).reshape(*lead, n_out)
+        if up2 is not None:
+            x2 = getattr(self.ops, "act_mul", F.act_mul)(x2, up2, act)
+        xq, s_x = self._quantize(x2)
         acc = self.ops.int_mm(xq, self.qweight)              # exact int32 partial sums of this K-slice
         if self.world > 1:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
@@ -393,9 +446,9 @@ class RowParallelDynamicQuantLinear(nn.Module):
 class ParallelGatedMLP(nn.Module):
     """Tensor-parallel gated MLP (Llama: down(silu(gate(x)) * up(x))) on the dynamic int8 path, Megatron layout:
     gate / up column-parallel with NO gather, the activation product computed on the local column slice, down
-    row-parallel with a K-sharded input.  Exchanges per forward: one all-reduce(MAX) of `tokens` floats (the
-    per-token scale of the hidden activation needs the row maximum over all shards) and the fused int32
-    reduce-scatter + all-gather of the down projection.  Because the hidden slices, the global row maxima and the
+    row-parallel with a K-sharded input.  Exchanges per forward: the row maxima of the hidden activation (`tokens`
+    floats per rank, through symmetric memory -- the per-token scale needs the maximum over all shards) and the fused
+    int32 reduce-scatter + all-gather of the down projection.  Because the hidden slices, the global row maxima and the
     int32 partial sums are all exact, the output is bit-identical to the same three DynamicQuantLinear modules
     chained on one GPU (with `act_mul_quant`'s definition of the activation product)."""
 
@@ -417,16 +470,42 @@ class ParallelGatedMLP(nn.Module):
         if (self.gate.lo, self.gate.hi) != (self.down.k_lo, self.down.k_hi):
             raise ValueError("column shards of gate/up and K shards of down do not line up")
 
+    def _gate_up(self, device):
+        """gate and up shards concatenated into ONE local DynamicQuantLinear ([2 * per, K] int8): one act-quant + one
+        GEMM per forward (per-output-channel scales make that exact).  Built on first use; not a registered submodule,
+        so `state_dict()` keeps the two shards only."""
+        gu = self.__dict__.get("_gu")
+        if gu is not None and gu.qweight_storage.device == device:
+            return gu
+        g, u = self.gate, self.up
+        if (g.bias is None) != (u.bias is None) or g.spec != u.spec:
+            return None
+        from .modules import DynamicQuantLinear
+        m = DynamicQuantLinear(g.in_features, 2 * g.per, g.bias is not None, device=device, out_dtype=self.out_dtype, spec=g.spec)
+        m.qweight_storage.copy_(torch.cat([g.qweight_storage, u.qweight_storage], dim=0))
+        m.weight_scale.copy_(torch.cat([g.weight_scale, u.weight_scale]))
+        if m.bias is not None:
+            m.bias.copy_(torch.cat([g.bias, u.bias]))
+        object.__setattr__(self, "_gu", m)
+        return m
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Two C calls per forward: pq_qlinear (act-quant + the fused gate/up GEMM on the local column slice) and
+        pq_rowparallel_forward with the gated input (silu(gate) * up computed, max-exchanged and quantised on the
+        fly, int32 GEMM + reduce-scatter + all-gather): 9 launches, no NCCL, no host sync -- CUDA-graph capturable."""
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         dt = self.out_dtype or x.dtype
-        xq, s_x = F.quantize_act(x2, spec=self.gate.spec)                 # one quantisation shared by gate and up
-        n = self.gate.hi - self.gate.lo
-        g = F.qgemm(xq, s_x, self.gate.qweight, self.gate.weight_scale, self.gate.bias, dt)[:, :n]
-        u = F.qgemm(xq, s_x, self.up.qweight, self.up.weight_scale, self.up.bias, dt)[:, :n]
-        h = F.act_mul(g, u, self.act)                                      # local slice of the hidden activation
-        y = self.down(h)
+        n, per = self.gate.hi - self.gate.lo, self.gate.per
+        gu_mod = self._gate_up(x2.device) if x2.is_cuda else None
+        if gu_mod is not None:
+            gu = gu_mod(x2)                                                # [M, 2 * per]
+            g, u = gu[:, :n], gu[:, per:per + n]
+        else:
+            xq, s_x = F.quantize_act(x2, spec=self.gate.spec)             # one quantisation shared by gate and up
+            g = F.qgemm(xq, s_x, self.gate.qweight, self.gate.weight_scale, self.gate.bias, dt)[:, :n]
+            u = F.qgemm(xq, s_x, self.up.qweight, self.up.weight_scale, self.up.bias, dt)[:, :n]
+        y = self.down(g, u, self.act)                                      # h = act(g) * u never leaves the kernels
         return y.reshape(*lead, self.down.out_features)
 
 
