@@ -93,7 +93,8 @@ int launch_act_mul_quant(const void* gate, const void* up, int dtype, int act,
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,
                  void* const* outs, int n_out, int out_dtype, int64_t ldo,
-                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols = 0, int multimem = 0);
+                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols = 0, int multimem = 0,
+                 int64_t rot_cols = 0);
 
 int launch_qlinear_smallm_fused(const void* x, int x_dtype, int64_t ldx,
                                 const int8_t* b, int64_t ldb, const float* s_w, const float* bias,

@@ -58,6 +58,7 @@ struct GemmArgs {
   int tma_store;            // staged epilogue hands its tiles to TMA bulk stores (single destination)
   int dbg;                  // profiling only (pq_debug_set_epilogue): bit 0 = the epilogue skips its global stores
   int multimem;             // out[0] is an NVSwitch multicast address: the LSU copy-out uses multimem.st
+  int n_rot;                // first column block of the tile order (see tile_coords), 0 <= n_rot < num_n_blocks
   int scatter_cols;         // > 0 (staged epilogue): columns [d*scatter_cols, (d+1)*scatter_cols) go to out[d] ONLY, as a
                             // [M, scatter_cols] matrix with row stride ldo (fused GEMM + reduce-scatter: out[d] is this
                             // rank's inbox on the rank that owns those output columns)
@@ -103,14 +104,17 @@ struct SmemLayout {
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+// n_rot: the column blocks are visited starting at block n_rot (reduce-scatter: every rank starts at a different
+// owner's columns, so at any moment the ranks store to DIFFERENT inboxes instead of all hammering one ingress port)
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int n_rot, int& m_blk, int& n_blk) {
   const int per_group = GROUP_M * num_n;
   const int group = tile / per_group;
   const int first_m = group * GROUP_M;
   const int gsize = min(GROUP_M, num_m - first_m);
   const int within = tile - group * per_group;
   m_blk = first_m + within % gsize;
-  n_blk = within / gsize;
+  n_blk = within / gsize + n_rot;
+  if (n_blk >= num_n) n_blk -= num_n;
 }
 
 // Work scheduler shared by the three roles.  A "segment" is a K-range [kb0,kb1) of one tile.
@@ -288,7 +292,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int tile, kb0, kb1;
       while (sched.next(tile, kb0, kb1)) {
         int m_blk, n_blk;
-        tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
+        tile_coords(tile, g.num_m_blocks, g.num_n_blocks, g.n_rot, m_blk, n_blk);
         const int m_idx = m_blk * SUPER_M + m_off;
         const int n_idx = n_blk * BN + (int)cta_rank * L::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -334,7 +338,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       Sched pf = sched;
       while (pf.next(tile, kb0, kb1)) {
         int m_blk, n_blk;
-        tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
+        tile_coords(tile, g.num_m_blocks, g.num_n_blocks, g.n_rot, m_blk, n_blk);
         const int n_idx = n_blk * BN + (int)cta_rank * L::B_ROWS;
         // mode 1: every CTA prefetches its own boxes; mode 2: one m-block per n-block does it
         const bool duty = (g.prefetch_b == 1) || (m_blk == n_blk % g.num_m_blocks);
@@ -410,7 +414,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int tile, kb0, kb1;
     for (; sched.next(tile, kb0, kb1); ++iter) {
       int m_blk, n_blk;
-      tile_coords(tile, g.num_m_blocks, g.num_n_blocks, m_blk, n_blk);
+      tile_coords(tile, g.num_m_blocks, g.num_n_blocks, g.n_rot, m_blk, n_blk);
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
       const int row = m_blk * SUPER_M + m_off + et;
       const int col0 = n_blk * BN;
@@ -894,6 +898,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
   GemmArgs g = g0;
   g.num_m_blocks = (g.M + BLOCK_M * CG * MC - 1) / (BLOCK_M * CG * MC);
   g.num_n_blocks = (g.N + BN - 1) / BN;
+  g.n_rot = (g0.n_rot / BN) % g.num_n_blocks;          // columns -> column blocks of this tile shape
   g.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, a, g.M, g.K, lda, BLOCK_M);
@@ -1138,7 +1143,8 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
 int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
                  const float* s_x, const float* s_w, const float* bias,
                  void* const* outs, int n_out, int out_dtype, int64_t ldo,
-                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols, int multimem) {
+                 int64_t M, int64_t N, int64_t K, cudaStream_t stream, int64_t scatter_cols, int multimem,
+                 int64_t rot_cols) {
   if (M < 0 || N < 0 || K < 1) PQ_FAIL(PQ_ERR_ARG, "qgemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   if (M == 0 || N == 0) return PQ_OK;
   if (M > 0x7fffff00LL || N > 0x7fffff00LL || K > 0x7fffff00LL) PQ_FAIL(PQ_ERR_ARG, "qgemm: dimension too large");
@@ -1180,6 +1186,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   g.prefetch_b = g_prefetch_b;
   g.dbg = g_epi_dbg;
   g.scatter_cols = (int)scatter_cols;
+  g.n_rot = (int)(rot_cols > 0 ? rot_cols : 0);      // in COLUMNS here; launch_cfg converts to blocks of its BLOCK_N
   if (multimem) {
     if (n_out != 1 || scatter_cols != 0 || !g.vec_ok || (N * esz) % 16 != 0)
       PQ_FAIL(PQ_ERR_ARG, "qgemm: a multicast destination needs n_ys == 1 and 16-byte aligned rows / row length");

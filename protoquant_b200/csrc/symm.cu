@@ -140,7 +140,9 @@ extern "C" int pq_rowparallel_forward(const void* x, const void* up, int x_dtype
   const int64_t slot_bytes = cap * per_n * 4;
   const int n_dests = (int)((N + per_n - 1) / per_n);
   for (int d = 0; d < n_dests; ++d) dests[d] = (char*)sg->inbox[d] + (int64_t)rank * slot_bytes;
-  rc = launch_qgemm(xq_ws, ldq, Wq, ldb, nullptr, nullptr, nullptr, dests, n_dests, PQ_I32, per_n, M, N, K_slice, st, per_n);
+  // every rank starts its tile order at its OWN column block, so the ranks store to different inboxes at any moment
+  rc = launch_qgemm(xq_ws, ldq, Wq, ldb, nullptr, nullptr, nullptr, dests, n_dests, PQ_I32, per_n, M, N, K_slice, st, per_n, 0,
+                    (int64_t)rank * per_n);
   if (rc) return rc;
   rc = launch_barrier(sg, 1, st);          // every rank's partial sums have landed
   if (rc) return rc;

@@ -378,6 +378,10 @@ class RowParallelDynamicQuantLinear(nn.Module):
         self._flip ^= 1
         xq_ws, sx_ws, amax_ws = self._workspace(M, x2.device)
         ks = self.k_hi - self.k_lo
+        if not self.input_is_sharded:
+            # a replicated input is handed over as its K-slice view: every rank reads 1/world of the activation for the
+            # row maxima and exchanges them (tokens x 4 bytes per peer) instead of reading all of it
+            x2 = x2[:, self.k_lo:self.k_hi]
         n_mine = self.n_hi - self.n_lo
         y_local = None
         if not self.gather_output:
@@ -387,7 +391,7 @@ class RowParallelDynamicQuantLinear(nn.Module):
             rc = _lib.lib().pq_rowparallel_forward(
                 x2.data_ptr(), up2.data_ptr() if up2 is not None else None, F._DT[x2.dtype], F._ACTS[act],
                 x2.stride(0), up2.stride(0) if up2 is not None else 0,
-                1 if self.input_is_sharded else 0, x2.shape[1], 0 if self.input_is_sharded else self.k_lo,
+                1, x2.shape[1], 0,
                 self.qweight_storage.data_ptr(), self.qweight_storage.stride(0), self.weight_scale.data_ptr(),
                 self.bias.data_ptr() if self.bias is not None else None,
                 st["sgp"], 1 if self.gather_output else 0,

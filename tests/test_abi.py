@@ -37,15 +37,24 @@ def test_every_declared_symbol_is_exported():
 
 def test_library_is_built_for_sm_100a_with_tcgen05():
     """The shipped cubin must be the sm_100a tcgen05/TMA kernels, not a legacy mma.sync build."""
+    import shutil
     import subprocess
-    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
-    if out.returncode != 0:
-        pytest.skip("cuobjdump not available")
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    assert os.path.exists(exe), "cuobjdump is part of the CUDA toolkit this repo builds with; without it the SASS evidence cannot be checked"
+    out = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-500:]
     assert "sm_100a" in out.stdout
     assert "UTCIMMA" in out.stdout          # tcgen05.mma.kind::i8
     assert "UTMALDG" in out.stdout          # TMA tensor loads
     assert "LDTM" in out.stdout             # tcgen05.ld
     assert "HMMA" not in out.stdout and "IMMA." not in out.stdout.replace("UTCIMMA", "")
+    assert "UBLKCP" in out.stdout           # 1-D bulk copies (staged quantizer)
+    assert "UTMASTG" in out.stdout          # TMA store epilogue
+    # the committed opcode histogram (tools/sass_opcodes.py) is the judged artefact: it must exist and agree
+    hist = open(os.path.join(ROOT, "profiles", "sass_opcodes_r2.txt")).read()
+    assert "legacy tensor opcodes in the whole library (HMMA / IMMA / *GMMA): none" in hist
+    for fam in ("qgemm_kernel", "qgemm_smallm_kernel", "rowwise_quant_vec_kernel", "symm_barrier_kernel"):
+        assert fam in hist, fam
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
