@@ -28,7 +28,18 @@ class QuantSpec:
         return PQQuantSpec(self.scale_mode, self.eps, self.qmin)
 
 
-DEFAULT_SPEC = QuantSpec()
+def _default_spec() -> QuantSpec:
+    """SPEC v0, unless tools/repin.py has pinned the knobs against the real reference (protoquant_b200/_pinned_spec.json)."""
+    import json
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_pinned_spec.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return QuantSpec(int(d["scale_mode"]), float(d["eps"]), int(d["qmin"]))
+    return QuantSpec()
+
+
+DEFAULT_SPEC = _default_spec()
 
 
 def _stream(device=None) -> ctypes.c_void_p:

@@ -168,6 +168,17 @@ def test_staged_quantizer_bit_exact(dtype, spec, ospec, shape):
         pq.lib().pq_debug_set_quant_staged(0)
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "reference_*.npz"))) or [None])
+def test_act_quant_matches_reference_golden(path):
+    """Vectors produced by the REAL reference (tools/repin.py --write).  None exist while the checkout is absent."""
+    if path is None:
+        pytest.skip("no reference_*.npz: the reference checkout is absent (SURVEY.md §0); tools/repin.py creates them")
+    d = np.load(path)
+    mode, eps, qmin = d["spec"]
+    q, s = pq.quantize_act(load_golden_x(d).cuda(), spec=pq.QuantSpec(int(mode), float(eps), int(qmin)))
+    assert np.array_equal(q.cpu().numpy(), d["q"]) and same_scales(s.cpu().numpy(), d["s"])
+
+
 def test_kat_round_half_even():
     x = torch.tensor([[127.0, 0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 3.49, -126.5, 126.5, 0.0, -127.0, 0, 0, 0, 0]])
     for dt in DTYPES:
