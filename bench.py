@@ -44,6 +44,7 @@ ACTS = {"x_attn": 4096, "attn_out": 4096, "x_mlp": 4096, "h_mlp": 11008}
 GROUPS = [("qkv_proj", ("q_proj", "k_proj", "v_proj"), "x_attn"), ("o_proj", ("o_proj",), "attn_out"),
           ("gate_up_proj", ("gate_proj", "up_proj"), "x_mlp"), ("down_proj", ("down_proj",), "h_mlp")]
 NVLINK_PEER_GBS = 770.0   # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)
+NVLINK_A2A_GBS = 645.0    # measured here: SM-issued stores, 8 GPUs pushing to all peers at once (profiles/nvlink_probe_n8_r2.log)
 S70_K, S70_N, S70_M = 8192, 28672, 2048
 OPS_PER_STEP = sum(2 * M_TOKENS * n * k for _, k, n, _ in LINEARS)
 NOMINAL_INT8_TOPS = 4500.0
@@ -665,32 +666,83 @@ def run_sharded(ctx):
         "nvlink_in_gbs_per_rank": in_gbs, "nvlink_frac_of_770": in_gbs / NVLINK_PEER_GBS, "per_rank_tops": rank_tops,
         "bytes_received_per_rank": bytes_in, "link_floor_ms": link_ms, "shard_gemm_floor_ms": gemm_ideal_ms,
         "target_ms": target_ms, "frac_of_target": target_ms / ms_per_step,
+        "nvlink_all_to_all_store_gbs_measured": NVLINK_A2A_GBS, "frac_of_measured_all_to_all": in_gbs / NVLINK_A2A_GBS,
+        "serial_model_ms": (M * (3 * K + 4) / (peaks["hbm_gbs"] * 1e9) + 2.0 * 256 * 256 * K / (2.0 * peaks["bf16_tflops"] * 1e12 / 74)) * 1e3
+                           + bytes_in / (NVLINK_A2A_GBS * 1e9) * 1e3 + 0.006,
+        "serial_model_note": "act-quant at HBM peak + the first 256x256 tile pair (nothing can be sent before it) + the bytes every rank "
+                             "must receive at the measured all-to-all store rate (tools/nvlink_probe.py: 645 GB/s per direction per GPU "
+                             "with all 8 GPUs pushing at once -- LSU stores, TMA bulk stores and multimem.st alike; the 770 GB/s figure "
+                             "is a pairwise copy-engine number) + one cross-rank barrier (6 us)",
         "peak_note": "the bound is the slower of (a) the bytes every rank must receive at 770 GB/s = measured peer-copy bandwidth per "
                      "direction per GPU (B200_PROFILING.md; nominal 900) and (b) the shard GEMM 2MNK/" + str(world) + " at 2 x measured cuBLAS bf16 "
                      f"burst ({peaks['bf16_tflops']} TF/s); frac_of_target = that floor / measured time",
     }
 
-    # ---- e2e: replicated input from pinned host memory on every rank, own output slice back to the host ----
+    # ---- e2e: the batch lives ONCE in pinned host memory; every step brings it in and takes the result out ----
+    # Every rank copies its 1/world block of the token rows host -> device (the H2D traffic is spread over all PCIe
+    # links), an all-gather over NVLink (NCCL) replicates the activation, the column-sharded layer runs through the
+    # public module API, and every rank copies ITS column slice of the gathered result device -> host.  Three streams,
+    # software-pipelined over steps (H2D + gather of step s+1 | kernels of step s | D2H of step s-1); every byte of
+    # every step crosses PCIe inside the timed region.
     lo, hi = shf.lo, shf.hi
-    host_x = x.cpu().pin_memory()
+    rows = M // world
+    host_x = x.cpu().pin_memory()                                  # the whole batch, as a host process would hold it
     host_y = torch.empty(M, hi - lo, dtype=torch.bfloat16).pin_memory()
-    x_dev = torch.empty_like(x)
+    x_part = [torch.empty(rows, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    x_devs = [torch.empty_like(x) for _ in range(2)]
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    compute_done, out_done = [None, None], [None, None]
+    step_no = [0]
 
     def e2e_step():
-        x_dev.copy_(host_x, non_blocking=True)
-        y = shf(x_dev)
-        host_y.copy_(y[:, lo:hi], non_blocking=True)
+        b = step_no[0] & 1
+        step_no[0] += 1
+        with torch.cuda.stream(copy_in):
+            if compute_done[b] is not None:
+                copy_in.wait_event(compute_done[b])               # step s-2 has consumed this activation buffer
+            x_part[b].copy_(host_x[rank * rows:(rank + 1) * rows], non_blocking=True)
+            dist.all_gather_into_tensor(x_devs[b], x_part[b])
+            ready = torch.cuda.Event()
+            ready.record(copy_in)
+        main.wait_event(ready)
+        if out_done[b] is not None:
+            main.wait_event(out_done[b])                          # the module's double-buffered output: step s-2 was read out
+        y = shf(x_devs[b])
+        done = torch.cuda.Event()
+        done.record(main)
+        compute_done[b] = done
+        with torch.cuda.stream(copy_out):
+            copy_out.wait_event(done)
+            host_y.copy_(y[:, lo:hi], non_blocking=True)
+            od = torch.cuda.Event()
+            od.record(copy_out)
+            out_done[b] = od
 
-    for _ in range(3):
+    def e2e_drain():
+        main.wait_stream(copy_out)
+        main.wait_stream(copy_in)
+
+    for _ in range(4):
         e2e_step()
+    e2e_drain()
     barrier()
-    e2e_steps = max(3, min(args.steps, 40))
-    e2e_ms = allmax(timed(torch, e2e_step, e2e_steps, warm=0) / e2e_steps)
+    e2e_steps = max(4, min(args.steps + (args.steps & 1), 40))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_drain()
+    t1.record()
+    barrier()
+    e2e_ms = allmax(t0.elapsed_time(t1) / e2e_steps)
     e2e_ok = bool(torch.equal(host_y, full(x)[:, lo:hi].cpu()))
-    e2e = {"value": ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "h2d_bytes_per_step": world * host_x.numel() * 2,
+    e2e = {"value": ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "h2d_bytes_per_step": M * K * 2,
            "d2h_bytes_per_step": M * N * 2, "ms_per_step": e2e_ms, "steps": e2e_steps, "output_matches": e2e_ok,
-           "note": "every rank copies the replicated activation in (pinned host -> device) and its own column slice of the result out"}
-    del host_x, host_y, x_dev
+           "note": "whole-job bytes: the batch is read from pinned host memory once per step (each rank copies its 1/world row block "
+                   "and an NVLink all-gather replicates it), every rank writes its own column slice of the result back; H2D, "
+                   "kernels and D2H of consecutive steps overlap on three streams"}
+    del host_x, host_y, x_devs, x_part
 
     # ---- side legs: NCCL vs fused at M = 16 / 2048, row-parallel down projection, gated MLP; tokens-sharded 7B step ----
     try:
