@@ -657,6 +657,13 @@ def run_sharded(ctx):
     in_gbs = bytes_in / (ms_per_step * 1e-3) / 1e9
     rank_tops = ops / world / (ms_per_step * 1e-3) / 1e12
     link_bound = link_ms >= gemm_ideal_ms
+    # serial model of the fused kernel: act-quant at HBM peak, then the slower of (first tile pair + the bytes to receive at the
+    # measured all-to-all store rate) and (whole waves of 256x256 tile pairs on 74 CTA pairs), then one cross-rank barrier
+    quant_ms_model = M * (3 * K + 4) / (peaks["hbm_gbs"] * 1e9) * 1e3
+    pair_ms = 2.0 * 256 * 256 * K / (2.0 * peaks["bf16_tflops"] * 1e12 / 74) * 1e3
+    pair_tiles = ((M + 255) // 256) * ((N // world + 255) // 256)
+    waves = (pair_tiles + 73) // 74
+    serial_ms = quant_ms_model + max(pair_ms + bytes_in / (NVLINK_A2A_GBS * 1e9) * 1e3, waves * pair_ms) + 0.006
     roofline = {
         "bound": "nvlink" if link_bound else "tensor",
         "kernel": "qgemm_kernel (tcgen05 GEMM, epilogue TMA-stores every tile into all ranks' symmetric output buffers over NVLink)",
@@ -667,10 +674,10 @@ def run_sharded(ctx):
         "bytes_received_per_rank": bytes_in, "link_floor_ms": link_ms, "shard_gemm_floor_ms": gemm_ideal_ms,
         "target_ms": target_ms, "frac_of_target": target_ms / ms_per_step,
         "nvlink_all_to_all_store_gbs_measured": NVLINK_A2A_GBS, "frac_of_measured_all_to_all": in_gbs / NVLINK_A2A_GBS,
-        "serial_model_ms": (M * (3 * K + 4) / (peaks["hbm_gbs"] * 1e9) + 2.0 * 256 * 256 * K / (2.0 * peaks["bf16_tflops"] * 1e12 / 74)) * 1e3
-                           + bytes_in / (NVLINK_A2A_GBS * 1e9) * 1e3 + 0.006,
-        "serial_model_note": "act-quant at HBM peak + the first 256x256 tile pair (nothing can be sent before it) + the bytes every rank "
-                             "must receive at the measured all-to-all store rate (tools/nvlink_probe.py: 645 GB/s per direction per GPU "
+        "serial_model_ms": serial_ms,
+        "frac_of_serial_model": serial_ms / ms_per_step, "tile_pair_waves": waves,
+        "serial_model_note": "act-quant at HBM peak + max(whole waves of 256x256 tile pairs on 74 CTA pairs; the first tile pair (nothing can "
+                             "be sent before it) + the bytes every rank must receive at the measured all-to-all store rate (tools/nvlink_probe.py: 645 GB/s per direction per GPU "
                              "with all 8 GPUs pushing at once -- LSU stores, TMA bulk stores and multimem.st alike; the 770 GB/s figure "
                              "is a pairwise copy-engine number) + one cross-rank barrier (6 us)",
         "peak_note": "the bound is the slower of (a) the bytes every rank must receive at 770 GB/s = measured peer-copy bandwidth per "
