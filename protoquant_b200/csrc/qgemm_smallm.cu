@@ -258,10 +258,13 @@ qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
 //      tcgen05.mma expects for its N operand (what TMA would have produced);
 //   meanwhile warp 0 is already streaming the weights -- they do not depend on x.
 // One launch instead of two, and xq / s_x never touch global memory.
-// STATUS: bit-exact and tested, but OFF by default -- on B200 it measured 13.5 us vs 9.6 us for the
-// two-kernel path at 16 x 4096 x 4096: every channel-tile cluster re-quantises x, and that puts two
-// dependent L2 round trips plus a cluster barrier on each CTA's critical path, whereas the separate
-// 1.6 us quantizer kernel overlaps the GEMM's weight prefetch through PDL.
+// STATUS: bit-exact and tested, but OFF by default -- on B200 it measures 14.5 us vs 10.3 us for the
+// two-kernel path at 16 x 4096 x 4096 (31 vs 17 us at N = 11008, 25 vs 12 us at 32 tokens): the cost scales with
+// the number of CTAs and with M, i.e. it is the REDUNDANT quantisation -- each of the 32 channel-tile clusters
+// re-quantises x, ~1000 instructions per quantising thread on every SM (round 2 replaced the shared-memory
+// atomicMax reduction by one warp per row: no change, so it was never the reduction) -- whereas the separate 2 us
+// quantizer kernel does the work once and overlaps the GEMM's weight prefetch through PDL.  A faster fusion has
+// to quantise once and publish (flag + TMA loads by the consumers); that saves one kernel boundary, ~1 us.
 struct FusedArgs {
   int M, N, K;
   int num_kb, splits;
@@ -395,22 +398,25 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
     if (k_hi > g.K) k_hi = g.K;
     const int vpr = (k_hi > k_lo) ? (k_hi - k_lo) / EPV : 0;    // 16-byte vectors per row in the slice
     const int nv = g.M * vpr;
-    constexpr int VB = 8;                                       // independent 16-byte loads in flight per thread
-    const bool resident = nv <= QTHREADS * VB;                  // the whole slice fits in registers: read x once
-    uint4 keep[VB];
-    auto load_vec = [&](int v) -> uint4 {
-      const int r = v / vpr, cv = v - r * vpr;
+    (void)nv;
+    // One WARP per row (rows qw, qw + 6, ...): lane l holds vectors l, l + 32, ... of the row's slice, the row maximum
+    // is a warp shuffle reduction -- the first version funnelled every vector through a shared-memory atomicMax on
+    // one of 16 addresses (a 32-way conflict per warp instruction), which alone cost several microseconds.
+    constexpr int QW = QTHREADS / 32;                            // quantising warps
+    constexpr int VL = 4;                                        // 16-byte vectors per lane and row kept in registers
+    constexpr int RPW = (MP + QW - 1) / QW;                      // rows per warp: 3 (MP = 16), 6, 11
+    constexpr int KEEP_ROWS = RPW <= 3 ? RPW : 1;
+    const int qw = warp - 2;
+    const bool resident = (RPW <= 3) && vpr <= 32 * VL;          // the warp's rows fit in registers: read x once
+    uint4 keep[KEEP_ROWS][VL];
+    auto load_rv = [&](int r, int cv) -> uint4 {
       return *reinterpret_cast<const uint4*>(x + (long long)r * g.ldx + k_lo + cv * EPV);
     };
-    auto vec_amax = [&](const uint4& raw) -> uint32_t {
-      float a;
-      if (sizeof(T) == 2) a = u16_mag_to_float<T>(absmax_u16x2(raw, 0u));
-      else a = vec_absmax<float>(raw, 0.f);
-      return __float_as_uint(a);                                // non-negative floats order like their bits
+    auto vec_amax = [&](const uint4& raw, uint32_t m) -> uint32_t {
+      if (sizeof(T) == 2) return absmax_u16x2(raw, m);           // packed u16 lanes, converted once per row
+      return __float_as_uint(vec_absmax<float>(raw, __uint_as_float(m)));
     };
-    auto quant_store = [&](int v, const uint4& raw) {
-      const int r = v / vpr, cv = v - r * vpr;
-      const RowQ rq = rowq[r];
+    auto quant_store = [&](int r, int cv, const uint4& raw, const RowQ& rq) {
       float f[EPV];
       unpack<T>(raw, f);
 #pragma unroll
@@ -428,19 +434,29 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
       }
     };
     // A. row |.|-max of the slice (all loads of a batch are issued before any is used)
-    for (int base = 0; base < nv; base += QTHREADS * VB) {
-      uint4 raw[VB];
 #pragma unroll
-      for (int i = 0; i < VB; ++i) {
-        const int v = base + qt + i * QTHREADS;
-        raw[i] = make_uint4(0, 0, 0, 0);
-        if (v < nv) raw[i] = load_vec(v);
-      }
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int r = qw + ri * QW;
+      if (r < g.M) {
+        uint32_t m = 0;
+        for (int c0 = 0; c0 < vpr; c0 += 32 * VL) {
+          uint4 raw[VL];
 #pragma unroll
-      for (int i = 0; i < VB; ++i) {
-        const int v = base + qt + i * QTHREADS;
-        if (v < nv) atomicMax(amax_loc + v / vpr, vec_amax(raw[i]));
-        keep[i] = raw[i];
+          for (int j = 0; j < VL; ++j) {
+            const int cv = c0 + (int)lane + 32 * j;
+            raw[j] = make_uint4(0, 0, 0, 0);
+            if (cv < vpr) raw[j] = load_rv(r, cv);
+          }
+#pragma unroll
+          for (int j = 0; j < VL; ++j) {
+            m = vec_amax(raw[j], m);
+            if (ri < KEEP_ROWS) keep[ri < KEEP_ROWS ? ri : 0][j] = raw[j];
+          }
+        }
+        if (sizeof(T) == 2) m = __float_as_uint(u16_mag_to_float<T>(m));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) amax_loc[r] = m;
       }
     }
     named_bar_sync(1, QTHREADS);
@@ -466,25 +482,32 @@ qlinear_smallm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Fu
     }
     named_bar_sync(1, QTHREADS);
     // B. quantise into the swizzled K-major operand layout
-    if (resident) {
 #pragma unroll
-      for (int i = 0; i < VB; ++i) {
-        const int v = qt + i * QTHREADS;
-        if (v < nv) quant_store(v, keep[i]);
-      }
-    } else {
-      for (int base = 0; base < nv; base += QTHREADS * VB) {
-        uint4 raw[VB];
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int r = qw + ri * QW;
+      if (r < g.M) {
+        const RowQ rq = rowq[r];
+        if (resident) {
 #pragma unroll
-        for (int i = 0; i < VB; ++i) {
-          const int v = base + qt + i * QTHREADS;
-          raw[i] = make_uint4(0, 0, 0, 0);
-          if (v < nv) raw[i] = load_vec(v);
-        }
+          for (int j = 0; j < VL; ++j) {
+            const int cv = (int)lane + 32 * j;
+            if (cv < vpr) quant_store(r, cv, keep[ri < KEEP_ROWS ? ri : 0][j], rq);
+          }
+        } else {
+          for (int c0 = 0; c0 < vpr; c0 += 32 * VL) {
+            uint4 raw[VL];
 #pragma unroll
-        for (int i = 0; i < VB; ++i) {
-          const int v = base + qt + i * QTHREADS;
-          if (v < nv) quant_store(v, raw[i]);
+            for (int j = 0; j < VL; ++j) {
+              const int cv = c0 + (int)lane + 32 * j;
+              raw[j] = make_uint4(0, 0, 0, 0);
+              if (cv < vpr) raw[j] = load_rv(r, cv);
+            }
+#pragma unroll
+            for (int j = 0; j < VL; ++j) {
+              const int cv = c0 + (int)lane + 32 * j;
+              if (cv < vpr) quant_store(r, cv, raw[j], rq);
+            }
+          }
         }
       }
     }
