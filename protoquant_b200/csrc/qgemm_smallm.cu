@@ -17,6 +17,7 @@
 #include "quant_math.cuh"
 
 namespace pq {
+Knob g_smallm_splits{0};  // pq_debug_set_smallm_splits: force the K-split (cluster size) of the decode GEMM; 0 = heuristic
 Knob g_fused_decode{0};   // pq_debug_set_fused_decode; OFF: measured slower than quant kernel + PDL (profiles/README_r1.md)
 namespace {
 
@@ -645,9 +646,13 @@ int launch_small(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, Sma
     PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(attr_err));
   const int n_tiles = (g.N + TILE_N - 1) / TILE_N;
   // Two CTAs fit per SM (<= 113 KB of shared memory each): split K until the grid fills those
-  // 2 x num_sms slots, keeping at least 4 K blocks per CTA.
+  // 2 x num_sms slots, keeping at least 4 K blocks per CTA -- or 1 when K is so short (<= 1024) that the launch is
+  // pure latency and more CTAs only shorten each one's chain (16 x 768 -> 3072: 6.9 -> 5.4 us, tools/decode_parts.py).
   int S = 1;
-  while (S < 8 && n_tiles * S * 2 <= 2 * num_sms && g.num_kb / (S * 2) >= 4) S *= 2;
+  const int min_kb = g.num_kb <= 8 ? 1 : 4;
+  while (S < 8 && n_tiles * S * 2 <= 2 * num_sms && g.num_kb / (S * 2) >= min_kb) S *= 2;
+  const int forced = g_smallm_splits;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) S = (forced <= g.num_kb) ? forced : 1;
   g.splits = S;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_tiles * S), 1, 1);
@@ -738,3 +743,5 @@ int launch_qlinear_smallm_fused(const void* x, int x_dtype, int64_t ldx,
 
 // Test/bench hook: 0 = never fuse the activation quantizer into the decode GEMM.
 extern "C" void pq_debug_set_fused_decode(int on) { pq::g_fused_decode = on; }
+
+extern "C" void pq_debug_set_smallm_splits(int s) { pq::g_smallm_splits = s; }
