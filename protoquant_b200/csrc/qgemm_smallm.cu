@@ -226,18 +226,30 @@ qgemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w,
       const int nl = (int)split * slice + (idx - m * slice);
       const int n = n_tile * TILE_N + nl;
       if (n >= g.N) continue;
+      // scales / bias first: their L2 round trip overlaps the distributed-shared-memory reads below instead of
+      // following them (the decode launch is a chain of dependent latencies, profiles/decode_parts_r2.log)
+      float sx = 0.f, sw = 0.f, bs = 0.f;
+      if constexpr (!RAW) {
+        sx = __ldg(g.s_x + m);
+        sw = __ldg(g.s_w + n);
+        if (g.bias != nullptr) bs = __ldg(g.bias + n);
+      }
       int acc = 0;
       if (S > 1) {
-        for (int p = 0; p < S; ++p) acc += ld_dsmem_s32(part_addr + (uint32_t)(m * TILE_N + nl) * 4u, (uint32_t)p);
+        int pa[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) pa[p] = (p < S) ? ld_dsmem_s32(part_addr + (uint32_t)(m * TILE_N + nl) * 4u, (uint32_t)p) : 0;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) acc += pa[p];
       } else {
         acc = part[m * TILE_N + nl];
       }
       float v = 0.f;
       if constexpr (!RAW) {
         v = __int2float_rn(acc);
-        v = __fmul_rn(v, __ldg(g.s_x + m));
-        v = __fmul_rn(v, __ldg(g.s_w + n));
-        if (g.bias != nullptr) v = __fadd_rn(v, __ldg(g.bias + n));   // no add at all without bias (-0.0 stays -0.0)
+        v = __fmul_rn(v, sx);
+        v = __fmul_rn(v, sw);
+        if (g.bias != nullptr) v = __fadd_rn(v, bs);   // no add at all without bias (-0.0 stays -0.0)
       }
       for (int d = 0; d < g.n_out; ++d) store_one<OutT>(g.out[d], (long long)m * g.ldo + n, v, acc);
     }
