@@ -22,6 +22,7 @@
 // 256 x BLOCK_N tile, each CTA stages its own 128 rows of A and its half of B, the even
 // CTA issues the MMAs for both and multicasts the commits.
 #include "gemm_common.cuh"
+#include <algorithm>
 #include <string.h>
 
 namespace pq {
@@ -203,7 +204,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
              const __grid_constant__ typename YMap<STAGED>::type tmap_y, const GemmArgs g) {
   using L = SmemLayout<CG, BN, STAGES, STAGED, std::is_same<OutT, int32_t>::value ? 0 : (int)sizeof(OutT)>;
   constexpr bool RAW = std::is_same<OutT, int32_t>::value;
-  static_assert(!STAGED || BN == 256, "staged epilogue assumes 128-column halves");
+  static_assert(!STAGED || (BN % 32 == 0 && BN >= 64), "staged epilogue works on whole 32-column chunks");
   static_assert(MC == 1 || (MC == 2 && CG == 2 && (BN / 4) % 8 == 0), "multicast clusters are pairs of CTA pairs");
   constexpr int SUPER_M = BLOCK_M * CG * MC;   // rows of one scheduled tile (all CTAs of the cluster)
   constexpr int UMMA_M = BLOCK_M * CG;
@@ -511,7 +512,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         constexpr int ESZ = (int)sizeof(OT);
         constexpr int COLS_PASS = ROWB / ESZ;                      // 128 (16-bit) or 64 (fp32)
         constexpr int CH_PASS = COLS_PASS / 32;
-        constexpr int PASSES = (BN / 2) / COLS_PASS;
+        // The left-half warps own chunks [0, CH), the right-half warps [CH, NCH) (CH = ceil(NCH / 2)): for BLOCK_N =
+        // 256 that is 128 + 128 columns, for 224 it is 128 + 96, for 128 it is 64 + 64.  Chunks >= c_hi do not exist.
+        constexpr int PASSES = (CH * 32 + COLS_PASS - 1) / COLS_PASS;
         constexpr int UPC = OutPack<OT>::WORDS / 4;                // 16-byte units per 32-column chunk
         constexpr int EPU = 16 / ESZ;                              // elements per 16-byte unit
         constexpr int SUB = 16384;                                 // bytes per sub-box
@@ -530,6 +533,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll 1
           for (int cc = 0; cc < CH_PASS; ++cc) {
             const int c = c_lo + pass * CH_PASS + cc;
+            if (c >= c_hi) break;                                  // narrower right half (warp-uniform)
             uint32_t r[32];
             tmem_ld_32x32(taddr0 + c * 32, r);
             tmem_ld_wait();
@@ -571,7 +575,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (CG == 1 || leader) mbar_arrive(bar_tempty + as * 8);
             else mbar_arrive_remote(bar_tempty + as * 8, leader_rank);
           }
-          const int colp = col0 + half * (BN / 2) + pass * COLS_PASS;
+          const int colp = col0 + c_lo * 32 + pass * COLS_PASS;
+          // columns this half staged in this pass (fewer than COLS_PASS for the narrower halves of BLOCK_N < 256)
+          const int cols_here = min((c_hi - c_lo) * 32 - pass * COLS_PASS, COLS_PASS);
           if (tma_out) {
             // one thread hands both sub-boxes to the TMA store engine: full-line writes, rows >= M and
             // columns >= N are clipped by the tensor map
@@ -607,21 +613,21 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const int rr = idx >> 4, u = idx & 15;
               const int grow = m0 + rr;
               const int gcol = colp + u * EPU;
-              if (grow < g.M && gcol < g.N) {
+              if (grow < g.M && gcol < n_end && u * EPU < cols_here) {
                 const uint4 v = *reinterpret_cast<const uint4*>(stg + (u >> 3) * SUB + rr * 128 + (((u & 7) ^ (rr & 7)) << 4));
                 if (g.scatter_cols > 0) {
                   // reduce-scatter: this 16-byte unit belongs to exactly one destination (scatter_cols % EPU == 0)
                   const int d = gcol / g.scatter_cols;
                   OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + (gcol - d * g.scatter_cols);
-                  if (g.vec_ok && gcol + EPU <= g.N) {
+                  if (g.vec_ok && gcol + EPU <= n_end) {
                     *reinterpret_cast<uint4*>(dst) = v;
                   } else {
                     const OT* ev = reinterpret_cast<const OT*>(&v);
 #pragma unroll
                     for (int e = 0; e < EPU; ++e)
-                      if (gcol + e < g.N) dst[e] = ev[e];
+                      if (gcol + e < n_end) dst[e] = ev[e];
                   }
-                } else if (g.vec_ok && gcol + EPU <= g.N) {
+                } else if (g.vec_ok && gcol + EPU <= n_end) {
                   if (g.multimem) {
                     multimem_st_v4(reinterpret_cast<OT*>(g.out[0]) + (long long)grow * g.ldo + gcol, v.x, v.y, v.z, v.w);
                   } else {
@@ -634,7 +640,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     OT* dst = reinterpret_cast<OT*>(g.out[d]) + (long long)grow * g.ldo + gcol;
 #pragma unroll
                     for (int e = 0; e < EPU; ++e)
-                      if (gcol + e < g.N) dst[e] = ev[e];
+                      if (gcol + e < n_end) dst[e] = ev[e];
                   }
                 }
               }
@@ -917,7 +923,8 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
     constexpr int esz = (int)sizeof(OutT);
     constexpr int subc = 128 / esz;
     const bool multi = g.n_out > 1 || g.scatter_cols > 0;
-    const bool want = tma_ok && !g.multimem && (!multi || g_multi_tma.load(std::memory_order_relaxed) != 0) &&
+    // (TMA boxes are whole 128-byte sub-boxes: only 256-wide tiles fill both halves exactly)
+    const bool want = BN == 256 && tma_ok && !g.multimem && (!multi || g_multi_tma.load(std::memory_order_relaxed) != 0) &&
                       (g.scatter_cols == 0 || g.scatter_cols % subc == 0);
     if (want) {
       bool ok = true;
@@ -1031,6 +1038,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
 }
 
 Knob g_force_cfg{-1};  // test hook: see pq_debug_set_gemm_config
+Knob g_multi_bn{0};    // multi-destination (staged) epilogues: tile width 256 / 224 / 128, 0 = model (pq_debug_set_multi_bn)
 Knob g_force_staged{0};  // test hook: staged epilogue even for a single destination
 Knob g_epi_dbg{0};       // profiling only: see GemmArgs::dbg
 Knob g_narrow_tiles{1};  // heuristic may pick BLOCK_N in {240, 224, 208} (pq_debug_set_narrow_tiles)
@@ -1053,8 +1061,33 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
   if ((g.n_out > 1 && !per_warp_multi) || g.scatter_cols > 0 || g.multimem ||
       (g_force_staged && !std::is_same<OutT, int32_t>::value)) {
     // fused all-gather / reduce-scatter: coalesced (shared-memory staged) stores to the peer destinations
-    if (g.M > 128) return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
-    return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+    if (g.M <= 128) return launch_cfg<1, 256, 3, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+    // Tile width (pq_debug_set_multi_bn forces one).  Model per width: the slower of (whole waves of tile pairs) and
+    // (first tile pair, before which nothing can be sent, + the bytes this rank stores to its peers at the measured
+    // all-to-all NVLink rate).  Compute-bound shards (2 GPUs) want the width with the fewest ragged waves (14336
+    // columns: 7 waves of 224 instead of 7 of 256), link-bound ones (>= 4 GPUs) the narrowest first tile.
+    int bn = g_multi_bn;
+    if (bn != 256 && bn != 224 && bn != 128) {
+      const double pair_rate = 3.0e15 / 74.0;                                   // int8 ops/s of one CTA pair (measured ~3000 TOPS)
+      const double esz = std::is_same<OutT, float>::value || std::is_same<OutT, int32_t>::value ? 4.0 : 2.0;
+      const int peers = g.scatter_cols > 0 ? 0 : (g.multimem ? 1 : g.n_out - 1);
+      const double egress = g.scatter_cols > 0 ? (double)g.M * g.N * esz * 0.875 : (double)peers * g.M * g.N * esz;
+      const double t_link = egress / 645.0e9;
+      static const int widths[3] = {256, 224, 128};
+      static const double eff[3] = {1.0, 1.0, 1.15};                            // narrower tiles load more operand bytes per MMA
+      double best = 1e30;
+      bn = 256;
+      for (int i = 0; i < 3; ++i) {
+        const double t_tile = 2.0 * 256.0 * widths[i] * g.K / pair_rate * eff[i];
+        const long long tiles = (long long)((g.M + 255) / 256) * ((g.N + widths[i] - 1) / widths[i]);
+        const long long waves = (tiles + num_sms / 2 - 1) / (num_sms / 2);
+        const double t = std::max((double)waves * t_tile, t_tile + t_link);
+        if (t < best * 0.97) { best = t; bn = widths[i]; }
+      }
+    }
+    if (bn == 224) return launch_cfg<2, 224, 5, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+    if (bn == 128) return launch_cfg<2, 128, 6, OutT, true>(a, lda, b, ldb, g, num_sms, st);
+    return launch_cfg<2, 256, 4, OutT, true>(a, lda, b, ldb, g, num_sms, st);
   }
   int cfg = g_force_cfg;
   if (cfg < 0) {
@@ -1240,3 +1273,4 @@ extern "C" void pq_debug_set_tma_store(int on) { pq::g_tma_store = on; }
 // device buffer of 40 x u64 per CTA (zeroed by the caller) receiving %globaltimer stamps, or null
 extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline.store(dev_buf, std::memory_order_relaxed); }
 extern "C" void pq_debug_set_multi_tma(int on) { pq::g_multi_tma = on; }
+extern "C" void pq_debug_set_multi_bn(int bn) { pq::g_multi_bn = bn; }

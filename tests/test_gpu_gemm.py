@@ -280,6 +280,34 @@ def test_qgemm_multi_tma_and_lsu_destinations_agree(shape, tma):
         assert not b[:, :off].any() and not b[:, off + N:].any() and not b[M:].any()
 
 
+@pytest.mark.parametrize("bn", [256, 224, 128])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(300, 512, 256), (2048, 3584, 1024), (129, 200, 384), (1000, 1000, 512), (513, 1400, 640)])
+def test_qgemm_multi_every_staged_tile_width(shape, out_dtype, bn):
+    """The multi-destination (CTA-staged, LSU copy-out) epilogue on its three tile widths -- 256, 224 (128 + 96 column
+    halves) and 128 (64 + 64): the launcher's model picks one per problem; here each is forced.  Ragged M / N, columns
+    outside the slice and rows past M stay untouched."""
+    from protoquant_b200 import functional as F
+    M, N, K = shape
+    N_total, off = N + 2 * 264, 264
+    esz = torch.empty(0, dtype=out_dtype).element_size()
+    g = torch.Generator().manual_seed(71)
+    xq, wq = rand_i8((M, K), 72).cuda(), rand_i8((N, K), 73).cuda()
+    s_x = (torch.rand(M, generator=g) * 0.1 + 1e-3).cuda()
+    s_w = (torch.rand(N, generator=g) * 0.01 + 1e-4).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = pq.qgemm(xq, s_x, wq, s_w, bias, out_dtype)
+    bufs = [torch.zeros(M + 3, N_total, dtype=out_dtype, device="cuda") for _ in range(3)]
+    pq.lib().pq_debug_set_multi_bn(bn)
+    try:
+        F.qgemm_multi(xq, s_x, wq, s_w, bias, [b.data_ptr() + off * esz for b in bufs], N_total, out_dtype)
+    finally:
+        pq.lib().pq_debug_set_multi_bn(0)
+    for b in bufs:
+        assert torch.equal(b[:M, off:off + N], ref)
+        assert not b[:, :off].any() and not b[:, off + N:].any() and not b[M:].any()
+
+
 def test_qlinear_multi_one_call_equals_qlinear():
     """pq_qlinear_multi (act-quant + multi-destination GEMM behind one C call) == pq_qlinear, bit for bit."""
     from protoquant_b200 import functional as F

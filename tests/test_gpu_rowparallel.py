@@ -45,13 +45,19 @@ def test_row_absmax_and_quantize_with_external_max(shape, dt):
 
 @pytest.mark.parametrize("shape,ndest", [((300, 512, 256), 3), ((100, 1000, 272), 4), ((2048, 4096, 1024), 8),
                                          ((16, 1024, 512), 2), ((129, 264, 144), 2)])
-def test_scatter_gemm_writes_each_column_block_to_its_destination(shape, ndest):
+@pytest.mark.parametrize("bn", [0, 256, 224, 128])
+def test_scatter_gemm_writes_each_column_block_to_its_destination(shape, ndest, bn):
+    """bn: tile width of the staged epilogue (0 = the launcher's model)."""
     M, N, K = shape
     a, b = rand_i8((M, K), 2).cuda(), rand_i8((N, K), 3).cuda()
     per = (-(-N // ndest) + 7) // 8 * 8
     ref = pq.qgemm_i32(a, b)
     inbox = torch.full((ndest, M, per), 7, dtype=torch.int32, device="cuda")
-    F.qgemm_i32_scatter(a, b, [inbox[d].data_ptr() for d in range(ndest)], per, per)
+    pq.lib().pq_debug_set_multi_bn(bn)
+    try:
+        F.qgemm_i32_scatter(a, b, [inbox[d].data_ptr() for d in range(ndest)], per, per)
+    finally:
+        pq.lib().pq_debug_set_multi_bn(0)
     for d in range(ndest):
         lo, hi = min(d * per, N), min((d + 1) * per, N)
         assert torch.equal(inbox[d][:, : hi - lo], ref[:, lo:hi])

@@ -65,13 +65,14 @@ for M in Ms:
     t_rep, _ = time_it(lambda: full(x))
     if rank == 0:
         print(f"M={M} world={world}: replicated {t_rep*1e3:.1f} us")
-    for label, env_mc, tma in (("tma_per_warp_boxes", None, 2), ("tma_staged_tile", None, 1), ("lsu_staged_tile", None, 0),
-                               ("multimem_st", "1", 1)):
+    for label, env_mc, tma, bn in (("lsu_staged_bn256", None, 0, 256), ("lsu_staged_bn224", None, 0, 224), ("lsu_staged_bn128", None, 0, 128),
+                                   ("lsu_staged_model", None, 0, 0), ("multimem_st_model", "1", 0, 0)):
         if env_mc:
             os.environ["PQ_USE_MULTICAST"] = env_mc
         else:
             os.environ.pop("PQ_USE_MULTICAST", None)
         pq.lib().pq_debug_set_multi_tma(tma)
+        pq.lib().pq_debug_set_multi_bn(bn)
         sh = pq.ShardedDynamicQuantLinear(wq, sw, None, fused=None)
         try:
             ok = all(torch.equal(sh(x), ref) for _ in range(3))
@@ -83,6 +84,7 @@ for M in Ms:
             print(f"  rank {rank} {label}: FAILED {ex!r}"[:300])
         del sh
     pq.lib().pq_debug_set_multi_tma(0)
+    pq.lib().pq_debug_set_multi_bn(0)
     os.environ.pop("PQ_USE_MULTICAST", None)
     shn = pq.ShardedDynamicQuantLinear(wq, sw, None, fused=False)
     t, mode = time_it(lambda: shn(x), graph=False)
