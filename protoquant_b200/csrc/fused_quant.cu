@@ -411,7 +411,11 @@ cudaError_t launch_pdl(void (*kern)(const Args), unsigned grid, unsigned block, 
 
 // (threads per row, 16-byte vectors per thread) covering nvec vectors with the fewest idle lanes;
 // the same scoring as rowwise_quant.cu restricted to the shapes instantiated here
+Knob g_fq_tpr{0}, g_fq_vpt{0};   // test hook (pq_debug_set_fused_quant_config): force (threads per row, vectors per thread)
+
 void pick_config(int nvec, long long M, int* tpr_out, int* vpt_out) {
+  const int ft = g_fq_tpr, fv = g_fq_vpt;
+  if (ft > 0 && fv > 0 && ft * fv >= nvec) { *tpr_out = ft; *vpt_out = fv; return; }
   static const int kVpt[4] = {4, 3, 6, 8};
   int best_tpr = 1024, best_vpt = 8;
   double best = 1e30;
@@ -561,3 +565,6 @@ int pq::launch_act_mul_quant(const void* gate, const void* up, int dtype, int ac
     default: return dispatch_cfg<__nv_bfloat16, ActLauncher>(a, M, a.nvec, st);
   }
 }
+
+// Test/bench hook: force the launch shape of norm_quant_kernel / act_mul_quant_kernel; 0,0 = heuristic.
+extern "C" void pq_debug_set_fused_quant_config(int tpr, int vpt) { pq::g_fq_tpr = tpr; pq::g_fq_vpt = vpt; }

@@ -145,3 +145,29 @@ def test_row_parallel_module_nvlink_bit_identical():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "ROWPARALLEL_OK" in p.stdout
+
+
+def test_symm_entry_points_validate_their_arguments():
+    """pq_symm_barrier / pq_rowparallel_forward refuse malformed groups instead of launching (world = 1 is a no-op
+    barrier; the one-call forward needs 2..8 ranks -- the multi-rank behaviour is covered by _rowparallel_worker.py
+    and by bench.py --gpus N, which fails the run on a mismatch)."""
+    import ctypes
+    from protoquant_b200 import _lib
+    lib = pq.lib()
+    pad = torch.zeros(64, dtype=torch.int32, device="cuda")
+    sg = _lib.PQSymmGroup()
+    sg.rank, sg.world, sg.cap = 0, 1, 16
+    sg.pads[0] = pad.data_ptr()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    before = pq.launch_count()
+    assert lib.pq_symm_barrier(ctypes.byref(sg), 0, st) == 0 and pq.launch_count() == before     # nothing to wait for
+    assert lib.pq_symm_barrier(ctypes.byref(sg), 9, st) == 1                                      # PQ_ERR_ARG: channel
+    sg.world = 3                                                                                   # pads of ranks 1, 2 missing
+    assert lib.pq_symm_barrier(ctypes.byref(sg), 0, st) == 1 and b"null signal pad" in lib.pq_last_error()
+    sg.world = 1
+    x = torch.zeros(16, 64, dtype=torch.bfloat16, device="cuda")
+    rc = lib.pq_rowparallel_forward(x.data_ptr(), None, 2, 0, 64, 0, 1, 64, 0, x.data_ptr(), 64, x.data_ptr(), None,
+                                    ctypes.byref(sg), 0, x.data_ptr(), 2, 64, x.data_ptr(), x.data_ptr(), None, 16, 64, 64, 64,
+                                    None, st)
+    assert rc == 1 and b"2..8 ranks" in lib.pq_last_error()
+    torch.cuda.synchronize()
