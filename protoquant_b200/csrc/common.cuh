@@ -42,6 +42,22 @@ extern Knob g_pdl;   // 1 = launch kernels with programmatic stream serializatio
               __FILE__, __LINE__);                                                     \
   } while (0)
 
+// Launch configuration with the programmatic-dependent-launch attribute (when enabled): the kernel may be scheduled
+// while its predecessor in the stream is still running and must execute griddepcontrol.wait before it touches
+// anything the predecessor produces.  `attr` must outlive the launch call.
+inline cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cfg;
+}
+
 // Checks that the current device is an sm_100 part; caches the answer per device.
 int check_device(int* num_sms);
 

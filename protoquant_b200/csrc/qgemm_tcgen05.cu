@@ -1071,7 +1071,8 @@ int launch_typed(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, con
       const double pair_rate = 3.0e15 / 74.0;                                   // int8 ops/s of one CTA pair (measured ~3000 TOPS)
       const double esz = std::is_same<OutT, float>::value || std::is_same<OutT, int32_t>::value ? 4.0 : 2.0;
       const int peers = g.scatter_cols > 0 ? 0 : (g.multimem ? 1 : g.n_out - 1);
-      const double egress = g.scatter_cols > 0 ? (double)g.M * g.N * esz * 0.875 : (double)peers * g.M * g.N * esz;
+      const double egress = g.scatter_cols > 0 ? (double)g.M * g.N * esz * (g.n_out - 1) / (double)g.n_out   // all but this rank's own block
+                                               : (double)peers * g.M * g.N * esz;
       const double t_link = egress / 645.0e9;
       static const int widths[3] = {256, 224, 128};
       static const double eff[3] = {1.0, 1.0, 1.15};                            // narrower tiles load more operand bytes per MMA

@@ -56,10 +56,11 @@ template <typename T>
 int launch_absmax(const void* x, int64_t M, int64_t K, int64_t ldx, const AmaxDst& dst, cudaStream_t st) {
   constexpr int EPV = VecTraits<T>::EPV;
   const bool vec = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) && ((ldx * (int64_t)sizeof(T)) % 16 == 0);
-  if (vec) row_absmax_kernel<T, true><<<(unsigned)M, 256, 0, st>>>((const T*)x, K, ldx, dst);
-  else row_absmax_kernel<T, false><<<(unsigned)M, 256, 0, st>>>((const T*)x, K, ldx, dst);
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg = pdl_config(dim3((unsigned)M), dim3(256), 0, st, attr);
+  if (vec) PQ_CUDA(cudaLaunchKernelEx(&cfg, row_absmax_kernel<T, true>, (const T*)x, K, ldx, dst));
+  else PQ_CUDA(cudaLaunchKernelEx(&cfg, row_absmax_kernel<T, false>, (const T*)x, K, ldx, dst));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  PQ_CUDA(cudaGetLastError());
   return PQ_OK;
 }
 
@@ -141,9 +142,10 @@ int launch_reduce(const ReduceArgs& a, cudaStream_t st) {
     for (int d = 0; d < a.n_ys; ++d) b.ys[d] = reinterpret_cast<O*>(a.ys[d]) + r0 * a.ldy;
     b.s_x = a.s_x + r0;
     dim3 grid((unsigned)((a.N + 1023) / 1024), (unsigned)nr);
-    reduce_dequant_kernel<O><<<grid, 256, 0, st>>>(b);
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = pdl_config(grid, dim3(256), 0, st, attr);
+    PQ_CUDA(cudaLaunchKernelEx(&cfg, reduce_dequant_kernel<O>, b));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    PQ_CUDA(cudaGetLastError());
   }
   return PQ_OK;
 }

@@ -32,6 +32,10 @@ __device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* addr, uint32_t cmp
 // order the peer stores of the kernels before the barrier against the loads of the kernels after it.
 // Every spin is bounded (wall clock): a rank that never arrives becomes a trap, not a hung GPU.
 __global__ void __launch_bounds__(32) symm_barrier_kernel(const Pads pads, int rank, int world, int channel) {
+  // launched with the PDL attribute: it may be scheduled early, so the launch latency is off the critical path, but
+  // it signals only after every earlier kernel of this stream has completed and its (peer) stores are visible
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   const int t = threadIdx.x;
   if (t >= world || t == rank) return;
   uint32_t* remote = pads.p[t] + channel * 8 + rank;
@@ -55,9 +59,10 @@ __global__ void __launch_bounds__(32) symm_barrier_kernel(const Pads pads, int r
 int launch_barrier(const pq_symm_group* sg, int channel, cudaStream_t st) {
   Pads p = {};
   for (int r = 0; r < sg->world; ++r) p.p[r] = sg->pads[r];
-  symm_barrier_kernel<<<1, 32, 0, st>>>(p, sg->rank, sg->world, channel);
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg = pdl_config(dim3(1), dim3(32), 0, st, attr);
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, symm_barrier_kernel, p, sg->rank, sg->world, channel));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  PQ_CUDA(cudaGetLastError());
   return PQ_OK;
 }
 
