@@ -105,7 +105,7 @@ def _declare(lib):
     if hasattr(lib, "pq_debug_set_timeline"):
         lib.pq_debug_set_timeline.restype = None
         lib.pq_debug_set_timeline.argtypes = [vp]
-    for dbg in ("pq_debug_set_gemm_config", "pq_debug_set_streamk", "pq_debug_set_pdl", "pq_debug_set_staged", "pq_debug_set_prefetch", "pq_debug_set_fused_decode", "pq_debug_set_tma_store", "pq_debug_set_epilogue", "pq_debug_set_narrow_tiles", "pq_debug_set_weight_prefetch", "pq_debug_set_multi_tma", "pq_debug_set_quant_staged", "pq_debug_set_smallm_splits", "pq_debug_set_multi_bn"):
+    for dbg in ("pq_debug_set_gemm_config", "pq_debug_set_streamk", "pq_debug_set_pdl", "pq_debug_set_staged", "pq_debug_set_prefetch", "pq_debug_set_fused_decode", "pq_debug_set_tma_store", "pq_debug_set_epilogue", "pq_debug_set_narrow_tiles", "pq_debug_set_weight_prefetch", "pq_debug_set_multi_tma", "pq_debug_set_quant_staged", "pq_debug_set_smallm_splits", "pq_debug_set_multi_bn", "pq_debug_set_tile_rotation"):
         if hasattr(lib, dbg):
             getattr(lib, dbg).restype = None
             getattr(lib, dbg).argtypes = [i32]

@@ -1038,6 +1038,7 @@ int launch_cfg(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb, const
 }
 
 Knob g_force_cfg{-1};  // test hook: see pq_debug_set_gemm_config
+Knob g_dbg_rot_cols{0};   // pq_debug_set_tile_rotation: first column of the tile order when the caller passes none
 Knob g_multi_bn{0};    // multi-destination (staged) epilogues: tile width 256 / 224 / 128, 0 = model (pq_debug_set_multi_bn)
 Knob g_force_staged{0};  // test hook: staged epilogue even for a single destination
 Knob g_epi_dbg{0};       // profiling only: see GemmArgs::dbg
@@ -1220,6 +1221,7 @@ int launch_qgemm(const int8_t* a, int64_t lda, const int8_t* b, int64_t ldb,
   g.prefetch_b = g_prefetch_b;
   g.dbg = g_epi_dbg;
   g.scatter_cols = (int)scatter_cols;
+  if (rot_cols <= 0) rot_cols = g_dbg_rot_cols;       // test hook: exercise the rotated tile order on one GPU
   g.n_rot = (int)(rot_cols > 0 ? rot_cols : 0);      // in COLUMNS here; launch_cfg converts to blocks of its BLOCK_N
   if (multimem) {
     if (n_out != 1 || scatter_cols != 0 || !g.vec_ok || (N * esz) % 16 != 0)
@@ -1275,3 +1277,4 @@ extern "C" void pq_debug_set_tma_store(int on) { pq::g_tma_store = on; }
 extern "C" void pq_debug_set_timeline(unsigned long long* dev_buf) { pq::g_timeline.store(dev_buf, std::memory_order_relaxed); }
 extern "C" void pq_debug_set_multi_tma(int on) { pq::g_multi_tma = on; }
 extern "C" void pq_debug_set_multi_bn(int bn) { pq::g_multi_bn = bn; }
+extern "C" void pq_debug_set_tile_rotation(int cols) { pq::g_dbg_rot_cols = cols; }

@@ -147,6 +147,35 @@ def test_row_parallel_module_nvlink_bit_identical():
     assert "ROWPARALLEL_OK" in p.stdout
 
 
+@pytest.mark.parametrize("rot", [0, 512, 1024, 1536, 4000])
+@pytest.mark.parametrize("shape", [(2048, 4096, 1024), (300, 1000, 272), (700, 2048, 512)])
+def test_rotated_tile_order_changes_nothing_but_the_order(shape, rot):
+    """The reduce-scatter GEMM of rank r visits the column blocks starting at ITS block (no ingress hot-spot on the
+    owners); any rotation must give the same bits -- scatter GEMM, plain GEMM with the fused epilogue, int32 output."""
+    M, N, K = shape
+    a, b = rand_i8((M, K), 12).cuda(), rand_i8((N, K), 13).cuda()
+    g = torch.Generator().manual_seed(14)
+    s_x = (torch.rand(M, generator=g) * 0.1 + 1e-3).cuda()
+    s_w = (torch.rand(N, generator=g) * 0.01 + 1e-4).cuda()
+    ref32 = pq.qgemm_i32(a, b)
+    ref16 = pq.qgemm(a, s_x, b, s_w, None, torch.bfloat16)
+    ndest = 4
+    per = (-(-N // ndest) + 7) // 8 * 8
+    pq.lib().pq_debug_set_tile_rotation(rot)
+    try:
+        inbox = torch.full((ndest, M, per), 7, dtype=torch.int32, device="cuda")
+        F.qgemm_i32_scatter(a, b, [inbox[d].data_ptr() for d in range(ndest)], per, per)
+        got32 = pq.qgemm_i32(a, b)
+        got16 = pq.qgemm(a, s_x, b, s_w, None, torch.bfloat16)
+    finally:
+        pq.lib().pq_debug_set_tile_rotation(0)
+    assert torch.equal(got32, ref32) and torch.equal(got16, ref16)
+    for d in range(ndest):
+        lo, hi = min(d * per, N), min((d + 1) * per, N)
+        assert torch.equal(inbox[d][:, : hi - lo], ref32[:, lo:hi])
+        assert bool((inbox[d][:, hi - lo:] == 7).all())
+
+
 def test_symm_entry_points_validate_their_arguments():
     """pq_symm_barrier / pq_rowparallel_forward refuse malformed groups instead of launching (world = 1 is a no-op
     barrier; the one-call forward needs 2..8 ranks -- the multi-rank behaviour is covered by _rowparallel_worker.py
