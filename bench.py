@@ -922,6 +922,24 @@ def bert_leg(pq, F, torch, dev):
         F.act_mul_quant(outs["ffn_up"], None, act="gelu", out=ws3072)   # GELU -> int8
         gemm("ffn_down", ws3072)
 
+    # what swap_linear(fuse_shared_inputs=True) builds for a BERT layer: query / key / value as ONE 768 -> 2304 GEMM
+    qkv = pq.fuse_linears([mods["q"], mods["k"], mods["v"]])
+    out_qkv = torch.empty(M, 2304, dtype=torch.bfloat16, device=dev)
+
+    def shared_input():
+        F.qlinear_into(x, qkv.qweight_storage, 768, qkv.weight_scale, qkv.bias, out_qkv, *ws768)
+        lin("o", ctx, ws768)
+        lin("ffn_up", outs["o"], ws768)
+        lin("ffn_down", outs["ffn_up"], ws3072)
+
+    def shared_input_fused_producers():
+        F.qlinear_into(x, qkv.qweight_storage, 768, qkv.weight_scale, qkv.bias, out_qkv, *ws768)
+        lin("o", ctx, ws768)
+        F.layernorm_quant(outs["o"], ln_w, ln_b, out=ws768)
+        gemm("ffn_up", ws768)
+        F.act_mul_quant(outs["ffn_up"], None, act="gelu", out=ws3072)
+        gemm("ffn_down", ws3072)
+
     tmp768 = torch.empty(M, 768, dtype=torch.bfloat16, device=dev)
     tmp3072 = torch.empty(M, 3072, dtype=torch.bfloat16, device=dev)
 
@@ -936,10 +954,13 @@ def bert_leg(pq, F, torch, dev):
         lin("ffn_down", tmp3072, ws3072)
 
     res = {"tokens": M, "linears": {n: [k, nn_] for n, k, nn_ in shapes},
-           "note": "act_quant_per_linear = the six linears alone (12 launches); with_torch_layernorm_gelu adds the two "
-                   "producer ops as torch kernels; fused_producers computes them inside the quantizing kernels (9 launches)"}
-    for label, fn in (("act_quant_per_linear", unfused), ("with_torch_layernorm_gelu", unfused_with_ops),
-                      ("fused_producers", fused)):
+           "note": "act_quant_per_linear = the six linears alone (12 launches); shared_input_fusion = the same work the way swap_linear sets a "
+                   "BERT layer up (query/key/value as one 768 -> 2304 GEMM: 8 launches); with_torch_layernorm_gelu adds LayerNorm and GELU "
+                   "as torch kernels in front of the quantizers; fused_producers computes them inside the quantizing kernels (9 launches); "
+                   "the last leg combines both fusions (8 launches, LayerNorm and GELU included)"}
+    for label, fn in (("act_quant_per_linear", unfused), ("shared_input_fusion", shared_input),
+                      ("with_torch_layernorm_gelu", unfused_with_ops), ("fused_producers", fused),
+                      ("shared_input_fusion_and_fused_producers", shared_input_fused_producers)):
         fn()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
