@@ -478,10 +478,12 @@ class ParallelGatedMLP(nn.Module):
         """gate and up shards concatenated into ONE local DynamicQuantLinear ([2 * per, K] int8): one act-quant + one
         GEMM per forward (per-output-channel scales make that exact).  Built on first use; not a registered submodule,
         so `state_dict()` keeps the two shards only."""
-        gu = self.__dict__.get("_gu")
-        if gu is not None and gu.qweight_storage.device == device:
-            return gu
         g, u = self.gate, self.up
+        # the copy is rebuilt when the shards change under it (load_state_dict, in-place edits): tensor version counters
+        key = (device,) + tuple(t._version for m in (g, u) for t in (m.qweight_storage, m.weight_scale, m.bias) if t is not None)
+        gu = self.__dict__.get("_gu")
+        if gu is not None and self.__dict__.get("_gu_key") == key:
+            return gu
         if (g.bias is None) != (u.bias is None) or g.spec != u.spec:
             return None
         from .modules import DynamicQuantLinear
@@ -491,6 +493,7 @@ class ParallelGatedMLP(nn.Module):
         if m.bias is not None:
             m.bias.copy_(torch.cat([g.bias, u.bias]))
         object.__setattr__(self, "_gu", m)
+        object.__setattr__(self, "_gu_key", key)
         return m
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -134,6 +134,10 @@ def test_parallel_gated_mlp_single_rank_equals_chained_modules():
     mlp = pq.ParallelGatedMLP(gate, up, down)
     assert torch.equal(mlp(x), want)
     assert torch.equal(mlp(x.reshape(4, 25, H)).reshape(M, H), want)
+    # the concatenated gate/up copy follows the shards: new weights loaded into the module are used by the next forward
+    gate2 = pq.DynamicQuantLinear.from_float(torch.nn.Linear(H, I, bias=False).to(torch.bfloat16).cuda())
+    mlp.gate.load_state_dict(pq.ShardedDynamicQuantLinear(gate2.qweight, gate2.weight_scale, None, gather_output=False, align=16).state_dict())
+    assert torch.equal(mlp(x), down(F.act_mul(gate2(x), up(x), "silu")))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
