@@ -303,6 +303,164 @@ rowwise_quant_generic_kernel(const T* __restrict__ x, int64_t M, int64_t K, int6
   }
 }
 
+// ---- transposed output in two launches: row scales, then [128 rows x 128 columns] tiles -----------------
+// The scale of a row needs the whole row, the transposed output wants many rows per CTA (R contiguous bytes per
+// output row) -- so the work is split: `row_scale_kernel` streams x once and writes s[m]; `transpose_tile_kernel`
+// re-reads x tile by tile (from L2 at activation sizes), derives the row parameters from s[m] alone, quantises,
+// turns 4 rows x 4 columns per lane into four words with PRMT, and writes 128 contiguous bytes per output row.
+// Small independent CTAs (52 KB of shared memory, 4 per SM): loads, arithmetic and stores of different tiles
+// overlap.  (An 8-CTA-cluster variant that kept an [R x K/8] slab resident and read x once was built and measured
+// 3-5x SLOWER: one 168 KB CTA per SM runs its phases in lock step, and only ~8 such clusters are co-resident.)
+// Same arithmetic (quant_math.cuh) => bit-identical codes and scales.
+constexpr int TT_ROWS = 128, TT_COLS = 128, TT_THREADS = 512;
+constexpr int TT_TP = TT_ROWS / 4 + 1;                // words per row of the transposed tile (odd)
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_scale_kernel(const T* __restrict__ x, int64_t K, int64_t ldx, float* __restrict__ s_out, int scale_mode, float eps, int vec) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  __shared__ float red[8];
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
+  const T* xr = x + (int64_t)blockIdx.x * ldx;
+  float amax = 0.f;
+  if (vec) {
+    const int64_t nvec = K / EPV;
+    if (sizeof(T) == 2) {
+      uint32_t m = 0;
+      for (int64_t v = threadIdx.x; v < nvec; v += 256) m = absmax_u16x2(ld_stream_16(xr + v * EPV), m);
+      amax = u16_mag_to_float<T>(m);
+    } else {
+      for (int64_t v = threadIdx.x; v < nvec; v += 256) amax = vec_absmax<float>(ld_stream_16(xr + v * EPV), amax);
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < K; k += 256) amax = mag_max(amax, mag_of((float)xr[k]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = mag_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) amax = mag_max(amax, red[w]);
+    s_out[blockIdx.x] = make_rowq(amax, scale_mode, eps).s;
+  }
+}
+
+// RowQ of the PQ_DIV / PQ_RCP_MUL modes from the stored scale alone (make_rowq derives everything but s from s there)
+__device__ __forceinline__ RowQ rowq_from_scale(float s, int mode) {
+  RowQ r;
+  r.s = s;
+  r.qmin = (mode & 0x100) ? -127.f : -128.f;
+  const bool safe = (s >= 0x1p-60f) && (s <= 0x1p60f);
+  r.mul = __frcp_rn(s);
+  r.path = ((mode & 0xff) == PQ_DIV) ? (safe ? 0 : 1) : (safe ? 2 : 3);
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TT_THREADS, 3)
+transpose_tile_kernel(const T* __restrict__ x, int64_t M, int64_t K, int64_t ldx, int8_t* __restrict__ xq_t, int64_t ldq,
+                      const float* __restrict__ s_in, int scale_mode, int vec) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr int ESZ = (int)sizeof(T);
+  constexpr int PITCH = TT_COLS * ESZ + 16;           // odd multiple of 16 bytes: row-strided 16-byte reads hit distinct banks
+  constexpr int WARPS = TT_THREADS / 32, QUADS = TT_ROWS / 4;
+  extern __shared__ __align__(16) uint8_t tt_smem[];       // slab [128][PITCH] | tile [128][33] u32 | rowq [128]
+  uint8_t* slab = tt_smem;
+  uint32_t* tile = reinterpret_cast<uint32_t*>(tt_smem + TT_ROWS * PITCH);
+  RowQ* rowq = reinterpret_cast<RowQ*>(tt_smem + TT_ROWS * PITCH + TT_COLS * TT_TP * 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.y * TT_ROWS, k0 = (int64_t)blockIdx.x * TT_COLS;
+  const int rows = (int)((M - row0 < TT_ROWS) ? M - row0 : TT_ROWS);
+  const int kw = (int)((K - k0 < TT_COLS) ? K - k0 : TT_COLS);
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
+  if (tid < TT_ROWS) rowq[tid] = rowq_from_scale(tid < rows ? __ldg(s_in + row0 + tid) : 1.0f, scale_mode);
+  if (vec) {
+    constexpr int VPR = TT_COLS / EPV;                // 16-byte vectors per tile row
+    constexpr int PER = TT_ROWS * VPR / TT_THREADS;   // 4 (16-bit) or 8 (fp32) vectors per thread, all requested up front
+    const int vw = kw / EPV;
+    uint4 raw[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int v = tid + i * TT_THREADS, r = v / VPR, cv = v % VPR;
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (r < rows && cv < vw) raw[i] = ld_stream_16(x + (row0 + r) * ldx + k0 + cv * EPV);
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int v = tid + i * TT_THREADS, r = v / VPR, cv = v % VPR;
+      *reinterpret_cast<uint4*>(slab + r * PITCH + cv * 16) = raw[i];
+    }
+  } else {
+    for (int e = tid; e < TT_ROWS * TT_COLS; e += TT_THREADS) {
+      const int r = e / TT_COLS, cc = e % TT_COLS;
+      T v = T(0.f);
+      if (r < rows && cc < kw) v = x[(row0 + r) * ldx + k0 + cc];
+      *reinterpret_cast<T*>(slab + r * PITCH + cc * ESZ) = v;
+    }
+  }
+  __syncthreads();
+  // quantise + transpose: warp task = one row quad x 128 columns; lane -> columns 4 lane .. 4 lane + 3
+  for (int quad = warp; quad < QUADS; quad += WARPS) {
+    const int kl = 4 * lane;
+    float f[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = quad * 4 + j;
+      const uint8_t* src = slab + r * PITCH + kl * ESZ;
+      if (sizeof(T) == 2) {
+        const uint2 w = *reinterpret_cast<const uint2*>(src);
+        if (std::is_same<T, __nv_bfloat16>::value) {
+          f[j][0] = __uint_as_float(w.x << 16); f[j][1] = __uint_as_float(w.x & 0xffff0000u);
+          f[j][2] = __uint_as_float(w.y << 16); f[j][3] = __uint_as_float(w.y & 0xffff0000u);
+        } else {
+          const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+          const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+          f[j][0] = a2.x; f[j][1] = a2.y; f[j][2] = b2.x; f[j][3] = b2.y;
+        }
+      } else {
+        const float4 t4 = *reinterpret_cast<const float4*>(src);
+        f[j][0] = t4.x; f[j][1] = t4.y; f[j][2] = t4.z; f[j][3] = t4.w;
+      }
+      const RowQ rq = rowq[r];
+      if (rq.path == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[j][q] = quant_fast(f[j][q], rq);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[j][q] = quant_any(f[j][q], rq);
+      }
+    }
+    // word for column kl + q: the codes of rows quad*4 .. +3 (little endian = ascending row = ascending address)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tile[(kl + q) * TT_TP + quad] = pack4(f[0][q], f[1][q], f[2][q], f[3][q]);
+  }
+  __syncthreads();
+  // write out: output row k0 + kk holds `rows` contiguous bytes at column row0
+  const bool full_rows = (rows == TT_ROWS) && (((uintptr_t)(xq_t + row0) & 3) == 0) && (ldq % 4 == 0);
+  if (full_rows) {
+    if (lane < QUADS) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(xq_t + (k0 + warp) * ldq + row0) + lane;
+      const int64_t step = (ldq / 4) * WARPS;
+      const uint32_t* src = tile + warp * TT_TP + lane;
+      int kk = warp;
+      for (; kk + 3 * WARPS < kw; kk += 4 * WARPS) {
+        const uint32_t w0 = src[0], w1 = src[WARPS * TT_TP], w2 = src[2 * WARPS * TT_TP], w3 = src[3 * WARPS * TT_TP];
+        dst[0] = w0; dst[step] = w1; dst[2 * step] = w2; dst[3 * step] = w3;
+        dst += 4 * step; src += 4 * WARPS * TT_TP;
+      }
+      for (; kk < kw; kk += WARPS) { *dst = *src; dst += step; src += WARPS * TT_TP; }
+    }
+  } else {
+    for (int kk = warp; kk < kw; kk += WARPS) {
+      int8_t* dst = xq_t + (k0 + kk) * ldq + row0;
+      for (int r = lane; r < rows; r += 32) dst[r] = (int8_t)((tile[kk * TT_TP + (r >> 2)] >> (8 * (r & 3))) & 0xffu);
+    }
+  }
+}
+
 // ---- transposed output, tiled: 32 rows per CTA ---------------------------------------
 // Pass 1 computes the 32 row scales (one warp per 4 rows, 16-byte loads when VEC); pass 2
 // re-reads the rows (L2 hits: the CTA just streamed them), quantises 32 x 128 tiles into
@@ -447,6 +605,32 @@ int launch_staged(const void* x, int64_t M, int nvec, int64_t ldx, int8_t* xq, i
 }
 
 template <typename T>
+int launch_transposed_two_pass(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq, float* s,
+                               const pq_quant_spec& spec, cudaStream_t st, bool vec) {
+  constexpr int DYN = TT_ROWS * (TT_COLS * (int)sizeof(T) + 16) + TT_COLS * TT_TP * 4 + TT_ROWS * (int)sizeof(RowQ);
+  static gemm::PerDeviceOnce once;
+  const cudaError_t e = once.run([&](int*) {
+    return cudaFuncSetAttribute(transpose_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN);
+  });
+  if (e != cudaSuccess) PQ_FAIL(PQ_ERR_CUDA, "cudaFuncSetAttribute(transposed quantizer) failed: %s", cudaGetErrorString(e));
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t c1 = pdl_config(dim3((unsigned)M), dim3(256), 0, st, attr);
+  PQ_CUDA(cudaLaunchKernelEx(&c1, row_scale_kernel<T>, (const T*)x, K, ldx, s, mode_bits(spec), spec.eps, vec ? 1 : 0));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  const int64_t kblocks = (K + TT_COLS - 1) / TT_COLS, rblocks = (M + TT_ROWS - 1) / TT_ROWS;
+  for (int64_t r0 = 0; r0 < rblocks; r0 += 65535) {          // grid.y limit
+    const int64_t nr = (rblocks - r0 < 65535) ? rblocks - r0 : 65535;
+    cudaLaunchAttribute attr2[1];
+    cudaLaunchConfig_t c2 = pdl_config(dim3((unsigned)kblocks, (unsigned)nr), dim3(TT_THREADS), (size_t)DYN, st, attr2);
+    const int64_t row_off = r0 * TT_ROWS;
+    PQ_CUDA(cudaLaunchKernelEx(&c2, transpose_tile_kernel<T>, (const T*)x + row_off * ldx, M - row_off, K, ldx, xq + row_off, ldq,
+                               (const float*)s + row_off, mode_bits(spec), vec ? 1 : 0));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  }
+  return PQ_OK;
+}
+
+template <typename T>
 int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64_t ldq,
              float* s, int transpose, const pq_quant_spec& spec, cudaStream_t st,
              const void* pf, long long pf_bytes, const float* amax_in, int amax_slots, long long amax_stride) {
@@ -455,6 +639,12 @@ int dispatch(const void* x, int64_t M, int64_t K, int64_t ldx, int8_t* xq, int64
   if (M > 0x7fffffffLL) PQ_FAIL(PQ_ERR_ARG, "rowwise quant: M=%lld too large", (long long)M);
   if (transpose) {
     if (amax_in) PQ_FAIL(PQ_ERR_UNSUPPORTED, "rowwise quant: an external row maximum cannot be combined with transpose");
+    // Two launches (row scales, then 128 x 128 tiles): every scale mode whose row parameters follow from the stored
+    // scale alone; PQ_INV_SCALE (needs amax itself) and pq_debug_set_quant_staged(-1) keep the 32-rows-per-CTA kernel.
+    if (spec.scale_mode != PQ_INV_SCALE && g_quant_staged >= 0 && K <= 0x7fffffffLL) {
+      const bool vec = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) && ((ldx * (int64_t)sizeof(T)) % 16 == 0);
+      return launch_transposed_two_pass<T>(x, M, K, ldx, xq, ldq, s, spec, st, vec);
+    }
     const int64_t grid = (M + 31) / 32;
     const bool tvec = (K % EPV == 0) && (((uintptr_t)x & 15) == 0) && ((ldx * (int64_t)sizeof(T)) % 16 == 0) &&
                       (((uintptr_t)xq & 15) == 0) && (ldq % 16 == 0);

@@ -79,9 +79,19 @@ def test_act_quant_strided_rows(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(5, 64), (70, 520), (33, 4096), (300, 100)])
-def test_act_quant_transposed_output(dtype, shape):
-    check(make_x(*shape, dtype, seed=5), *SPECS[0], transpose=True)
+@pytest.mark.parametrize("kernel", ["two_pass", "tiled"])
+@pytest.mark.parametrize("shape", [(5, 64), (70, 520), (33, 4096), (300, 100), (2048, 4096), (1000, 11008), (129, 8192),
+                                   (130, 1000), (64, 28672), (4100, 768)])
+def test_act_quant_transposed_output(dtype, shape, kernel):
+    """transpose=1: codes written as [K, M].  "two_pass" (default): a row-scale launch, then [128 x 128] tiles quantised
+    and transposed through shared memory (128 contiguous bytes per output row; aligned or not, ragged M / K);
+    "tiled": the single-launch 32-rows-per-CTA kernel (kept for PQ_INV_SCALE, whose row parameters need amax itself)."""
+    pq.lib().pq_debug_set_quant_staged(0 if kernel == "two_pass" else -1)
+    try:
+        for spec, ospec in SPECS if shape[0] <= 300 else SPECS[:1]:
+            check(make_x(*shape, dtype, seed=5), spec, ospec, transpose=True)
+    finally:
+        pq.lib().pq_debug_set_quant_staged(0)
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "torch_ao_*.npz"))))
@@ -94,7 +104,7 @@ def test_act_quant_matches_committed_golden(path):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "exact_*.npz"))))
-@pytest.mark.parametrize("kernel", ["vec", "staged", "generic", "transposed", "given_amax"])
+@pytest.mark.parametrize("kernel", ["vec", "staged", "generic", "transposed", "transposed_tiled", "given_amax"])
 def test_act_quant_matches_exact_rational_golden(path, kernel):
     """Default spec (and the other knob sets) against the exact-rational producer, including the NaN / inf /
     denormal-scale rows, through each quantizer kernel: the register-resident vector kernel, the generic one
@@ -114,8 +124,12 @@ def test_act_quant_matches_exact_rational_golden(path, kernel):
             big = torch.zeros(M, K + 3, dtype=x.dtype)
             big[:, 1:K + 1] = x                        # rows start at an odd element: no 16-byte alignment
             q, s = pq.quantize_act(big.cuda()[:, 1:K + 1], spec=spec)
-        elif kernel == "transposed":
-            q, s = pq.quantize_act(x.cuda(), transpose=True, spec=spec)
+        elif kernel in ("transposed", "transposed_tiled"):
+            pq.lib().pq_debug_set_quant_staged(0 if kernel == "transposed" else -1)
+            try:
+                q, s = pq.quantize_act(x.cuda(), transpose=True, spec=spec)
+            finally:
+                pq.lib().pq_debug_set_quant_staged(0)
             q = q.t()
         else:
             amax = F.row_absmax(x.cuda())
