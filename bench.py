@@ -445,7 +445,18 @@ def run_single(ctx):
     roofline["act_quant_stream_gbs"] = gbs
     roofline["act_quant_stream_frac"] = gbs / peaks["hbm_gbs"]
     roofline["act_quant_stream_shape"] = [Mbig, Kbig]
-    del xb, qb, sb
+    # optional transposed output of the quantizer ([K, M]; two launches: row scales, then 128 x 128 tiles -- x is read twice)
+    qt_big = F.alloc_q(Kbig, Mbig, dev)
+    t_ms = timed(torch, lambda: F.quantize_act(xb, transpose=True, out=(qt_big, sb)), 5)
+    roofline["act_quant_transposed_stream_frac"] = 5 * Mbig * (3 * Kbig + 4) / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]
+    del xb, qb, sb, qt_big
+    qt = F.alloc_q(4096, M_TOKENS, dev)
+    st_ = torch.empty(M_TOKENS, dtype=torch.float32, device=dev)
+    t_run, _ = capture(torch, dev, lambda: [F.quantize_act(acts[a], transpose=True, out=(qt, st_)) for a in ("x_attn", "attn_out", "x_mlp")], args.no_graph)
+    t_us = timed(torch, t_run, 20) / 60 * 1e3
+    roofline["act_quant_transposed_2048x4096_us"] = t_us
+    roofline["act_quant_transposed_2048x4096_frac"] = M_TOKENS * (3 * 4096 + 4) / (t_us * 1e-6) / 1e9 / peaks["hbm_gbs"]
+    del qt, st_
 
     # ---- sustained regime: at least one second of back-to-back steps (the chip reaches its 1 kW power cap) ----
     sust_steps = int(min(20000, max(200, 1.2 / (ms_per_step * 1e-3))))
