@@ -67,3 +67,54 @@ def test_gemm_any_shape(M, N, k16, seed):
     y = pq.qgemm(a.cuda(), s_x.cuda(), b.cuda(), s_w.cuda(), None, torch.bfloat16)
     want = O.cast_out(O.dequant_epilogue(ref, s_x.numpy(), s_w.numpy(), None), "bf16")
     assert torch.equal(y.cpu().view(torch.int16), want.view(torch.int16))
+
+
+@settings(**COMMON)
+@given(rows=st.integers(1, 700), k8=st.integers(1, 1500), dti=st.integers(0, 2), pad=st.sampled_from([0, 0, 8, 16]),
+       seed=st.integers(0, 10 ** 6))
+def test_staged_quantizer_any_shape(rows, k8, dti, pad, seed):
+    """The persistent shared-memory staged quantizer forced on: any row count (slot refills, fewer groups than slots),
+    any 16-byte-multiple row length, strided rows."""
+    dt = DTS[dti]
+    K = k8 * 8
+    x = _x(rows, K, dt, seed, pad)[:, :K]
+    pq.lib().pq_debug_set_quant_staged(1)
+    try:
+        q, s = pq.quantize_act(x.cuda())
+    finally:
+        pq.lib().pq_debug_set_quant_staged(0)
+    q_o, s_o = O.quantize_rowwise(x)
+    assert np.array_equal(q.cpu().numpy(), q_o) and np.array_equal(s.cpu().numpy(), s_o)
+
+
+@settings(**COMMON)
+@given(M=st.integers(65, 600), n8=st.integers(1, 120), k16=st.integers(1, 24), bn=st.sampled_from([0, 256, 224, 128]),
+       ndest=st.integers(2, 4), rot=st.sampled_from([0, 0, 256, 520]), seed=st.integers(0, 10 ** 6))
+def test_multi_destination_and_scatter_gemm_any_shape(M, n8, k16, bn, ndest, rot, seed):
+    """Fused all-gather (every destination gets the tile) and reduce-scatter (column block d goes to destination d)
+    epilogues on every staged tile width, with a rotated tile order: the bits of the plain GEMM, nothing else touched."""
+    from protoquant_b200 import functional as F
+    N, K = n8 * 8, k16 * 16
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).cuda()
+    b = torch.randint(-128, 128, (N, K), dtype=torch.int8, generator=g).cuda()
+    s_x = (torch.rand(M, generator=g) * 0.1 + 1e-3).cuda()
+    s_w = (torch.rand(N, generator=g) * 0.01 + 1e-4).cuda()
+    ref16 = pq.qgemm(a, s_x, b, s_w, None, torch.bfloat16)
+    ref32 = pq.qgemm_i32(a, b)
+    per = (-(-N // ndest) + 7) // 8 * 8
+    pq.lib().pq_debug_set_multi_bn(bn)
+    pq.lib().pq_debug_set_tile_rotation(rot)
+    try:
+        bufs = [torch.zeros(M + 2, N + 16, dtype=torch.bfloat16, device="cuda") for _ in range(ndest)]
+        F.qgemm_multi(a, s_x, b, s_w, None, [t.data_ptr() + 16 for t in bufs], N + 16, torch.bfloat16)
+        inbox = torch.full((ndest, M, per), 7, dtype=torch.int32, device="cuda")
+        F.qgemm_i32_scatter(a, b, [inbox[d].data_ptr() for d in range(ndest)], per, per)
+    finally:
+        pq.lib().pq_debug_set_multi_bn(0)
+        pq.lib().pq_debug_set_tile_rotation(0)
+    for t in bufs:
+        assert torch.equal(t[:M, 8:8 + N], ref16) and not t[:, :8].any() and not t[:, 8 + N:].any() and not t[M:].any()
+    for d in range(ndest):
+        lo, hi = min(d * per, N), min((d + 1) * per, N)
+        assert torch.equal(inbox[d][:, : hi - lo], ref32[:, lo:hi]) and bool((inbox[d][:, hi - lo:] == 7).all())
