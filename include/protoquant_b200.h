@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PQ_VERSION 100 /* 0.1.0 */
+#define PQ_VERSION 200 /* 0.2.0: round 2 added pq_qlinear_multi, pq_symm_barrier, pq_rowparallel_forward (additive; every 0.1.0 entry point is unchanged) */
 
 enum pq_dtype { PQ_F32 = 0, PQ_F16 = 1, PQ_BF16 = 2, PQ_I32 = 3 };
 

@@ -23,7 +23,7 @@ def declared_symbols():
 
 def test_library_loads_and_reports_version():
     lib = pq.lib()
-    assert lib.pq_version() == 100
+    assert lib.pq_version() == 200
 
 
 def test_every_declared_symbol_is_exported():
