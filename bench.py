@@ -769,6 +769,17 @@ def run_sharded(ctx):
         sharded = {"error": repr(ex)[:300]}
     barrier()
     clocks = sampler.result()
+    # parity gate, part 2: every multi-GPU side leg (NCCL vs fused at 16 / 2048 tokens, row-parallel down projection, gated MLP)
+    # must have reproduced the single-GPU bits on every rank
+    flags = [sharded.get("M16_bit_identical"), sharded.get("M2048_bit_identical"),
+             (sharded.get("down_proj_row_parallel") or {}).get("bit_identical"),
+             (sharded.get("gated_mlp_8192_28672") or {}).get("bit_identical")] if "error" not in sharded else []
+    # (a side leg that raised is reported in the line as {"error": ...} and does not take the headline down; a leg that RAN
+    # and produced different bits does)
+    if allmax(1.0 if any(f is False for f in flags) else 0.0):
+        if rank == 0:
+            sys.stderr.write(f"bench: a multi-GPU leg differs from the single-GPU result ({flags}) -- failing the run\n")
+        return 3
     if rank == 0:
         line = {
             "metric": "int8_qlinear_tops", "value": value, "unit": "TOPS", "n_gpus": world, "steps": steps,
