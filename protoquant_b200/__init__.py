@@ -9,13 +9,13 @@ from .functional import (DEFAULT_SPEC, QuantSpec, act_mul_quant, dequantize as d
 from .modules import DynamicQuantLinear, SharedInputLinear, fuse_linears, swap_linear
 from .qtensor import QTensor, dequantize, quantize
 from .sharded import (ParallelGatedMLP, RowParallelDynamicQuantLinear, ShardedDynamicQuantLinear, TokenAdaptiveLinear,
-                      maybe_shard, shard_bounds)
+                      maybe_shard, parallelize_gated_mlps, shard_bounds)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = [
     "ProtoquantError", "launch_count", "lib", "QuantSpec", "DEFAULT_SPEC",
     "quantize_act", "quantize_weight", "qgemm", "qgemm_i32", "qlinear", "dequantize_tensor",
     "norm_quant", "rmsnorm_quant", "layernorm_quant", "act_mul_quant",
     "QTensor", "quantize", "dequantize", "DynamicQuantLinear", "SharedInputLinear", "swap_linear", "fuse_linears",
-    "ShardedDynamicQuantLinear", "RowParallelDynamicQuantLinear", "ParallelGatedMLP", "TokenAdaptiveLinear", "maybe_shard", "shard_bounds",
+    "ShardedDynamicQuantLinear", "RowParallelDynamicQuantLinear", "ParallelGatedMLP", "TokenAdaptiveLinear", "maybe_shard", "parallelize_gated_mlps", "shard_bounds",
 ]

@@ -516,6 +516,38 @@ class ParallelGatedMLP(nn.Module):
         return y.reshape(*lead, self.down.out_features)
 
 
+_HF_ACTS = {"SiLU": "silu", "SiLUActivation": "silu", "GELU": "gelu", "GELUActivation": "gelu", "NewGELUActivation": "gelu_tanh",
+            "PytorchGELUTanh": "gelu_tanh", "GELUTanh": "gelu_tanh", "Identity": "identity"}
+
+
+def parallelize_gated_mlps(model: nn.Module, group=None, names=("gate_proj", "up_proj", "down_proj"), act_attr: str = "act_fn",
+                           out_dtype: Optional[torch.dtype] = None, spec: Optional[F.QuantSpec] = None,
+                           fused: Optional[bool] = None) -> int:
+    """Replace, in place, every sub-module of `model` that is a gated MLP -- children `names` = (gate, up, down) that are
+    nn.Linear (or DynamicQuantLinear) and an activation module `act_attr` (Hugging Face's LlamaMLP / MistralMLP / Qwen2MLP
+    layout) -- by a tensor-parallel `ParallelGatedMLP` over `group`.  Every rank calls it on the SAME full model (CUDA);
+    each keeps its shards only.  Returns the number of modules replaced.  `forward(x)` keeps its signature.  The result
+    equals the single-GPU chain `down(act_mul(gate(x), up(x)))` of this package bit for bit; against the float module it
+    differs by the int8 quantisation (and by one bf16 ulp on a few elements: SiLU is evaluated in fp32 here)."""
+    from .modules import DynamicQuantLinear
+    replaced = 0
+    for name, child in list(model.named_children()):
+        parts = [getattr(child, n, None) for n in names]
+        if all(isinstance(p, (nn.Linear, DynamicQuantLinear)) for p in parts):
+            act_mod = getattr(child, act_attr, None)
+            act = _HF_ACTS.get(type(act_mod).__name__) if act_mod is not None else "identity"
+            if isinstance(act_mod, nn.GELU) and getattr(act_mod, "approximate", "none") == "tanh":
+                act = "gelu_tanh"
+            if act is None:
+                raise ValueError(f"{name}: unsupported activation {type(act_mod).__name__} (silu / gelu / gelu_tanh / identity)")
+            q = [p if isinstance(p, DynamicQuantLinear) else DynamicQuantLinear.from_float(p, out_dtype=out_dtype, spec=spec) for p in parts]
+            setattr(model, name, ParallelGatedMLP(q[0], q[1], q[2], group=group, act=act, out_dtype=out_dtype, fused=fused))
+            replaced += 1
+        else:
+            replaced += parallelize_gated_mlps(child, group, names, act_attr, out_dtype, spec, fused)
+    return replaced
+
+
 class TokenAdaptiveLinear(nn.Module):
     """Keeps the replicated DynamicQuantLinear next to its column-sharded twin and picks per call by token count:
     calls with fewer than `min_tokens` tokens run on the replicated copy.  Round 1 needed this (M = 16 on 8 GPUs:

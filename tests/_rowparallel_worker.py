@@ -122,6 +122,28 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 if rank == 0:
                     print(f"TIMING llama70b_mlp 8192/28672 M=2048 world={dist.get_world_size()} {name}: {t.item()*1e3:.1f} us")
+    # Hugging Face's own LlamaMLP converted in place: same bits as this package's single-GPU chain, close to the float module
+    try:
+        from transformers.models.llama.modeling_llama import LlamaConfig, LlamaMLP
+        import copy
+        hf = LlamaMLP(LlamaConfig(hidden_size=1024, intermediate_size=2816, num_attention_heads=8, num_hidden_layers=1, vocab_size=64))
+        hf = hf.to(torch.bfloat16).cuda().eval()
+        xh = torch.randn(96, 1024, dtype=torch.bfloat16, device="cuda")
+        with torch.no_grad():
+            y_float = hf(xh)
+            holder = torch.nn.ModuleDict({"mlp": copy.deepcopy(hf)})
+            n_rep = pq.parallelize_gated_mlps(holder)
+            y_tp = holder["mlp"](xh)
+            g1, u1, d1 = (pq.DynamicQuantLinear.from_float(getattr(hf, n)) for n in ("gate_proj", "up_proj", "down_proj"))
+            y_one = d1(F.act_mul(g1(xh), u1(xh), "silu"))
+        same = n_rep == 1 and isinstance(holder["mlp"], pq.ParallelGatedMLP) and torch.equal(y_tp, y_one)
+        close = (y_tp.float() - y_float.float()).abs().max().item() < 0.08 * y_float.float().abs().max().item() + 1e-3
+        ok = ok and same and close
+        if rank == 0:
+            print(f"HF LlamaMLP -> ParallelGatedMLP: replaced={n_rep} bit_identical_to_one_gpu_chain={same} close_to_float={close}")
+    except ImportError:
+        if rank == 0:
+            print("transformers not importable: HF drop-in check skipped")
     # timing: Llama-70B down projection 28672 -> 8192 at 2048 tokens
     N, K, M = 8192, 28672, 2048
     lin = torch.nn.Linear(K, N, bias=False).to(torch.bfloat16).cuda()
