@@ -359,3 +359,27 @@ def test_token_adaptive_linear_dispatches_by_token_count():
     m = pq.TokenAdaptiveLinear(Rec("replicated"), Rec("sharded"), min_tokens=128)
     m(torch.zeros(16, 8)); m(torch.zeros(4, 32, 8)); m(torch.zeros(2, 8, 8))
     assert calls == ["replicated", "sharded", "replicated"]
+
+
+def test_parallelize_gated_mlps_finds_the_hf_layout_and_maps_the_activation():
+    from torch import nn
+
+    class MLP(nn.Module):
+        def __init__(self, act):
+            super().__init__()
+            self.gate_proj, self.up_proj = pq.DynamicQuantLinear(64, 160, bias=False), pq.DynamicQuantLinear(64, 160, bias=False)
+            self.down_proj = pq.DynamicQuantLinear(160, 64, bias=False)
+            self.act_fn = act
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mlp, self.other = MLP(nn.SiLU()), nn.Linear(8, 8)
+
+    model = nn.ModuleList([Block(), Block()])
+    assert pq.parallelize_gated_mlps(model) == 2
+    assert all(isinstance(b.mlp, pq.ParallelGatedMLP) and b.mlp.act == "silu" and isinstance(b.other, nn.Linear) for b in model)
+    tanh = nn.ModuleDict({"m": MLP(nn.GELU(approximate="tanh"))})
+    assert pq.parallelize_gated_mlps(tanh) == 1 and tanh["m"].act == "gelu_tanh"
+    with pytest.raises(ValueError, match="unsupported activation"):
+        pq.parallelize_gated_mlps(nn.ModuleDict({"m": MLP(nn.Tanh())}))
