@@ -202,7 +202,109 @@ def make_rows(name: str, K: int, seed: int) -> np.ndarray:
     return np.stack(bits)
 
 
+# ---- dequant epilogue (row a4) and QTensor.dequantize (row a5), exact --------------------------------------
+def f32_add(a, b):
+    (sa, va), (sb, vb) = a, b
+    if va == NAN or vb == NAN:
+        return 0, NAN
+    if va == INF or vb == INF:
+        if va == INF and vb == INF:
+            return (0, NAN) if sa != sb else (sa, INF)
+        return (sa, INF) if va == INF else (sb, INF)
+    x = (-va if sa else va) + (-vb if sb else vb)
+    if x == 0:
+        return (sa & sb), Fraction(0)          # (+0) + (-0) = +0 in round-to-nearest; (-0) + (-0) = -0
+    return (1 if x < 0 else 0), round_to_f32(abs(x))
+
+
+def round_to(v: Fraction, mbits: int, emin: int, emax: int):
+    """Round a non-negative rational to a binary format with `mbits` mantissa bits (RNE); INF on overflow."""
+    if v == 0:
+        return Fraction(0)
+    n, d = v.numerator, v.denominator
+    e = n.bit_length() - d.bit_length()
+    if Fraction(2) ** e > v:
+        e -= 1
+    elif Fraction(2) ** (e + 1) <= v:
+        e += 1
+    e = max(e, emin)
+    ulp = Fraction(2) ** (e - mbits)
+    q, r = divmod(v, ulp)
+    q = int(q)
+    if r * 2 > ulp or (r * 2 == ulp and (q & 1)):
+        q += 1
+    out = q * ulp
+    return INF if out >= Fraction(2) ** (emax + 1) else out
+
+
+def bits_of(sign, v, ebits, mbits):
+    bias = (1 << (ebits - 1)) - 1
+    top = sign << (ebits + mbits)
+    if v == NAN:
+        return ((1 << ebits) - 1) << mbits | (1 << (mbits - 1))
+    if v == INF:
+        return top | (((1 << ebits) - 1) << mbits)
+    if v == 0:
+        return top
+    n, d = v.numerator, v.denominator
+    e = n.bit_length() - d.bit_length()
+    if Fraction(2) ** e > v:
+        e -= 1
+    elif Fraction(2) ** (e + 1) <= v:
+        e += 1
+    if e < 1 - bias:
+        m = v / Fraction(2) ** (1 - bias - mbits)
+        assert m.denominator == 1
+        return top | int(m)
+    m = (v / Fraction(2) ** e - 1) * (1 << mbits)
+    assert m.denominator == 1
+    return top | ((e + bias) << mbits) | int(m)
+
+
+def epilogue_exact(acc: int, sx_bits: int, sw_bits: int, b_bits):
+    """((float(acc) * s_x) * s_w) + bias, every step rounded to binary32; returns (sign, value)."""
+    t = (1 if acc < 0 else 0, round_to_f32(Fraction(abs(acc))))          # int32 -> fp32, RNE
+    t = f32_mul(t, decode(sx_bits, 8, 23))
+    t = f32_mul(t, decode(sw_bits, 8, 23))
+    if b_bits is not None:
+        t = f32_add(t, decode(b_bits, 8, 23))
+    return t
+
+
+def make_epilogue_golden():
+    g = np.random.default_rng(2024)
+    M, N = 24, 40
+    acc = g.integers(-(2 ** 26), 2 ** 26, (M, N), dtype=np.int64)
+    acc[0, :8] = [0, 1, -1, 16777217, -16777217, 2 ** 31 - 1, -(2 ** 31), 33554433]     # not representable in fp32 / extremes
+    acc[1] = g.integers(-300, 300, N)                                                  # small sums: results near the bias
+    sx = (g.random(M) * 0.1 + 1e-3).astype(np.float32); sx[2] = np.float32(1e-30); sx[3] = np.float32(3e30)
+    sw = (g.random(N) * 0.01 + 1e-4).astype(np.float32); sw[5] = np.float32(1e-20); sw[6] = np.float32(2e10)
+    bias = g.standard_normal(N).astype(np.float32); bias[7] = np.float32(-0.0); bias[8] = np.float32(65504.0)
+    out = {"acc": acc.astype(np.int32), "s_x": sx, "s_w": sw, "bias": bias}
+    for tag, use_bias in (("bias", True), ("nobias", False)):
+        y32 = np.zeros((M, N), np.uint32); y16 = np.zeros((M, N), np.uint16); yb16 = np.zeros((M, N), np.uint16)
+        for m in range(M):
+            for n in range(N):
+                s_, v = epilogue_exact(int(acc[m, n]), int(sx[m].view(np.uint32)), int(sw[n].view(np.uint32)),
+                                       int(bias[n].view(np.uint32)) if use_bias else None)
+                y32[m, n] = f32_bits(s_, v)
+                y16[m, n] = bits_of(s_, v if v in (INF, NAN) else round_to(v, 10, -14, 15), 5, 10)
+                yb16[m, n] = bits_of(s_, v if v in (INF, NAN) else round_to(v, 7, -126, 127), 8, 7)
+        out[f"y_f32_{tag}"], out[f"y_f16_{tag}"], out[f"y_bf16_{tag}"] = y32, y16, yb16
+    # dequantize: q * s, one rounding
+    q = g.integers(-128, 128, (M, N), dtype=np.int64).astype(np.int8)
+    dq = np.zeros((M, N), np.uint32)
+    for m in range(M):
+        for n in range(N):
+            s_, v = f32_mul((1 if q[m, n] < 0 else 0, Fraction(abs(int(q[m, n])))), decode(int(sx[m].view(np.uint32)), 8, 23))
+            dq[m, n] = f32_bits(s_, v)
+    out["q"], out["dequant_rows_f32"] = q, dq
+    np.savez_compressed(os.path.join(HERE, "epilogue_exact_24x40.npz"), **out)
+    print("wrote epilogue_exact_24x40.npz")
+
+
 def main():
+    make_epilogue_golden()
     for name in ("f32", "bf16", "f16"):
         ebits, mbits = FMT[name]
         for K in (40, 96):

@@ -193,6 +193,24 @@ def test_act_quant_matches_reference_golden(path):
     assert np.array_equal(q.cpu().numpy(), d["q"]) and same_scales(s.cpu().numpy(), d["s"])
 
 
+@pytest.mark.parametrize("out,key", [(torch.float32, "f32"), (torch.bfloat16, "bf16"), (torch.float16, "f16")])
+def test_epilogue_and_dequantize_match_exact_rational_golden(out, key):
+    """The dequant epilogue as a stand-alone kernel (pq_reduce_dequant on one int32 part) and pq_dequant against the
+    exact-rational producer: same bits for fp32, bf16 and fp16 outputs (overflow -> inf included)."""
+    d = np.load(os.path.join(GOLDEN, "epilogue_exact_24x40.npz"))
+    acc = torch.from_numpy(d["acc"]).cuda()
+    sx, sw, bias = (torch.from_numpy(d[k]).cuda() for k in ("s_x", "s_w", "bias"))
+    for tag, b in (("bias", bias), ("nobias", None)):
+        y = F.dequant_accumulators(acc, sx, sw, b, out_dtype=out).cpu()
+        got = y.view(torch.int32).numpy().view(np.uint32) if out == torch.float32 else y.view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(got, d[f"y_{key}_{tag}"]), tag
+    if out == torch.float32:
+        q = F.alloc_q(*d["q"].shape, "cuda")
+        q.copy_(torch.from_numpy(d["q"]))
+        dq = pq.dequantize_tensor(q, sx, axis=0, out_dtype=torch.float32).cpu().view(torch.int32).numpy().view(np.uint32)
+        assert np.array_equal(dq, d["dequant_rows_f32"])
+
+
 def test_kat_round_half_even():
     x = torch.tensor([[127.0, 0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 3.49, -126.5, 126.5, 0.0, -127.0, 0, 0, 0, 0]])
     for dt in DTYPES:

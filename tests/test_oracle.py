@@ -43,6 +43,28 @@ def test_oracle_matches_exact_rational_golden(path):
         assert same_scales(s, d["s_" + label].view(np.float32)), label
 
 
+def test_epilogue_and_dequantize_match_exact_rational_golden(clib):
+    """Rows a4 / a5 against the exact-rational producer: ((float(acc) * s_x) * s_w) + bias with every step rounded to
+    binary32, then ONE rounding to bf16 / fp16 (overflow -> inf), incl. accumulators that fp32 cannot represent, tiny and
+    huge scales, a -0.0 bias; numpy oracle and C restatement."""
+    d = np.load(os.path.join(GOLDEN, "epilogue_exact_24x40.npz"))
+    acc, sx, sw = d["acc"], d["s_x"], d["s_w"]
+    M, N = acc.shape
+    with np.errstate(over="ignore"):
+        for tag, b in (("bias", d["bias"]), ("nobias", None)):
+            y = O.dequant_epilogue(acc, sx, sw, b)
+            assert np.array_equal(y.view(np.uint32), d["y_f32_" + tag])
+            assert np.array_equal(O.cast_out(y, "bf16").view(torch.int16).numpy().view(np.uint16), d["y_bf16_" + tag])
+            assert np.array_equal(O.cast_out(y, "f16").view(torch.int16).numpy().view(np.uint16), d["y_f16_" + tag])
+            yc = np.empty((M, N), np.float32)
+            accc, bc = np.ascontiguousarray(acc), (np.ascontiguousarray(b) if b is not None else None)
+            clib.pqo_epilogue_f32(accc.ctypes.data_as(ctypes.c_void_p), sx.ctypes.data_as(ctypes.c_void_p),
+                                  sw.ctypes.data_as(ctypes.c_void_p), bc.ctypes.data_as(ctypes.c_void_p) if bc is not None else None,
+                                  ctypes.c_int64(M), ctypes.c_int64(N), yc.ctypes.data_as(ctypes.c_void_p))
+            assert np.array_equal(yc.view(np.uint32), d["y_f32_" + tag])
+    assert np.array_equal(O.dequantize(d["q"], sx, 0).view(np.uint32), d["dequant_rows_f32"])
+
+
 def test_nonfinite_policy_kat():
     """NaN / inf propagate into the scale; the row's codes are all zero.  A scale that underflows to 0 saturates."""
     x = np.array([[1.0, -2.0, np.inf, 0.5], [1.0, np.nan, -np.inf, 0.0], [3e-45, -3e-45, 0.0, 1.4e-45]], np.float32)
