@@ -25,6 +25,14 @@ against protoquant itself.  What it follows instead:
   committed golden vectors from those torch ops, and ``tests/test_oracle.py`` pins
   this oracle against them.
 
+* Exact-rational golden vectors (``tests/golden/make_golden_exact.py`` -> ``exact_*.npz``,
+  ``epilogue_exact_24x40.npz``): every binary32 operation of SPEC v0 done in exact rational
+  arithmetic + integer round-to-nearest-even -- a third, independent producer that pins the
+  DEFAULT spec (and the other knob sets), the non-finite / denormal policy, the dequant
+  epilogue and dequantize.  It pins this module to the written spec, still not to protoquant.
+* ``tools/repin.py <reference_root>`` re-pins the knobs against the real reference the day it
+  is mounted.
+
 All arithmetic is explicit numpy float32 (no fused multiply-add, no fast-math).
 """
 from __future__ import annotations
