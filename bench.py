@@ -16,7 +16,7 @@ N = 1 -- workload "llama7b_linears_2048tok" (BASELINE.json configs[2]): one "ste
             (torch._int_mm) on the same shapes in the same run; act-quant against the measured HBM peak.
 N > 1 -- workload "llama70b_up_proj_colsharded_2048tok" (BASELINE.json configs[3], north_star (4)): the Llama-70B
   up projection 8192 -> 28672 column-sharded over the N GPUs, 2048 tokens, all-gather of the output slices
-  INCLUDED (fused into the GEMM epilogue: TMA stores into every rank's symmetric output buffer over NVLink,
+  INCLUDED (fused into the GEMM epilogue: coalesced peer stores into every rank's symmetric output buffer over NVLink,
   one cross-rank barrier).  Total work is fixed -> "scaling": "strong".  value = 2*M*N*K / time (max over ranks);
   roofline.bound = "nvlink": bytes every rank must receive / time against the measured 770 GB/s peer bandwidth.
   The sharded output is compared bit for bit with the replicated layer on every rank; a mismatch fails the run.
@@ -677,7 +677,7 @@ def run_sharded(ctx):
     serial_ms = quant_ms_model + max(pair_ms + bytes_in / (NVLINK_A2A_GBS * 1e9) * 1e3, waves * pair_ms) + 0.006
     roofline = {
         "bound": "nvlink" if link_bound else "tensor",
-        "kernel": "qgemm_kernel (tcgen05 GEMM, epilogue TMA-stores every tile into all ranks' symmetric output buffers over NVLink)",
+        "kernel": "qgemm_kernel<staged> (tcgen05 GEMM, epilogue stores every tile into all ranks' symmetric output buffers over NVLink: coalesced 256-byte LSU peer stores)",
         "achieved": in_gbs if link_bound else rank_tops, "peak": NVLINK_PEER_GBS if link_bound else 2.0 * peaks["bf16_tflops"],
         "unit": "GB/s" if link_bound else "TFLOP/s",
         "frac": (in_gbs / NVLINK_PEER_GBS) if link_bound else rank_tops / (2.0 * peaks["bf16_tflops"]), "traffic": None,
@@ -787,7 +787,7 @@ def run_sharded(ctx):
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": "llama70b_up_proj_colsharded_2048tok", "tokens": M, "layer": [K, N], "act_dtype": "bf16",
                        "out_dtype": "bf16", "launches_per_step": launches_per_step,
-                       "parallelism": f"column-parallel x{world}: act-quant (replicated) + shard GEMM whose epilogue TMA-stores every tile "
+                       "parallelism": f"column-parallel x{world}: act-quant (replicated) + shard GEMM whose epilogue stores every tile "
                                       "into all ranks' output buffers over NVLink (fused all-gather) + 1 cross-rank barrier",
                        "launch": launch_mode,
                        "l2": "per-rank working set (weight shard + activation + 117 MB gathered output) is larger than L2"},

@@ -126,7 +126,8 @@ int pq_qgemm_multi(const int8_t* xq, int64_t lda, const int8_t* Wq, int64_t ldb,
  * followed by the fused GEMM + all-gather store (as pq_qgemm_multi).  flags: PQ_MULTI_MULTICAST = ys[0] is an NVSwitch
  * multicast address (n_ys must be 1): the epilogue then writes it with multimem.st and the switch replicates the
  * tile into every rank; without the flag every ys[d] is a unicast (local or NVLink peer-mapped) address and is
- * written with TMA bulk stores.  Two kernel launches, no sync; the caller issues the cross-rank barrier. */
+ * written from the CTA-staged tile with coalesced 256-byte peer stores (measured faster over NVLink than TMA
+ * stores; the tile width 256 / 224 / 128 is chosen per launch).  Two kernel launches, no sync; the caller issues the cross-rank barrier. */
 enum pq_multi_flags { PQ_MULTI_MULTICAST = 1 };
 int pq_qlinear_multi(const void* x, int x_dtype, int64_t ldx,
                      const int8_t* Wq, int64_t ldb, const float* s_w, const float* bias,

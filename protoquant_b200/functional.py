@@ -255,7 +255,7 @@ def qlinear_multi_into(x2: torch.Tensor, wq_storage: torch.Tensor, in_features: 
                        multicast: bool = False) -> None:
     """One `pq_qlinear_multi` call: act-quant into the caller's workspace + GEMM whose epilogue stores the [M, N]
     result into every raw device address of `dest_ptrs` (row stride `ldy` elements): the local output buffer and
-    the peers' buffers over NVLink (TMA bulk stores), or, with `multicast`, one NVSwitch multicast address
+    the peers' buffers over NVLink (coalesced 256-byte peer stores from the CTA-staged tile), or, with `multicast`, one NVSwitch multicast address
     (multimem.st).  The caller issues the cross-rank barrier afterwards."""
     _require_cuda(x2, "x")
     M, N, K = x2.shape[0], wq_storage.shape[0], in_features
