@@ -238,6 +238,12 @@ class _OracleShardOps:
         return torch.from_numpy(O.int_mm(xq.numpy(), wq.numpy()))
 
     @staticmethod
+    def act_mul(g, u, act):
+        # T(T(act(gate)) * up): the definition of protoquant_b200.act_mul, in fp64 then rounded twice like the kernel
+        a = torch.from_numpy(O.act_ref(O.to_f32(g).astype(np.float64), act)).to(g.dtype)
+        return (a.double() * u.double()).to(g.dtype)
+
+    @staticmethod
     def epilogue(acc, s_x, s_w, bias, out_dtype):
         name = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[out_dtype]
         return O.cast_out(O.dequant_epilogue(acc.numpy(), s_x.numpy(), s_w.numpy(), None if bias is None else bias.numpy()), name)
@@ -263,6 +269,14 @@ def _row_worker(rank, world, port, N, K, M, q):
                 y = lin(xin)
                 want = full if gather else full[:, lin.n_lo:lin.n_hi]
                 ok = ok and torch.equal(y, want)
+        # gated input (the MLP's down projection): y = down(act(gate) * up) with K-sharded gate / up slices
+        gate = torch.randn(M, K).to(torch.bfloat16)
+        up = torch.randn(M, K).to(torch.bfloat16)
+        h = _OracleShardOps.act_mul(gate, up, "silu")
+        want = O.qlinear(h, wq, sw, b.numpy(), out_dtype="bf16")
+        lin = pq.RowParallelDynamicQuantLinear(torch.from_numpy(wq), torch.from_numpy(sw), b, ops=_OracleShardOps, input_is_sharded=True)
+        y = lin(gate[:, lin.k_lo:lin.k_hi].contiguous(), up[:, lin.k_lo:lin.k_hi].contiguous(), "silu")
+        ok = ok and torch.equal(y, want)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
